@@ -1,0 +1,617 @@
+// dsb_api.cu -- host side of the C ABI declared in include/disimpy_b200.h.
+// Owns device memory, the stream and the launch sequence; no PyTorch, no Python.
+#include "../../include/disimpy_b200.h"
+#include "dsb_fill.cuh"
+#include "dsb_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define DSB_CUDA(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? DSB_ENOMEM : DSB_ECUDA,                 \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
+    } while (0)
+
+// ------------------------------------------------------------- xoroshiro128+ jump matrices
+
+struct HState {
+    uint64_t s0, s1;
+};
+
+inline uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+inline void h_next(HState &s)
+{
+    uint64_t s0 = s.s0, s1 = s.s1;
+    s1 ^= s0;
+    s.s0 = rotl(s0, 55) ^ s1 ^ (s1 << 14);
+    s.s1 = rotl(s1, 36);
+}
+
+// numba/cuda/random.py:102-126 (the published xoroshiro128+ 2^64 jump polynomial)
+inline HState h_jump(HState s)
+{
+    static const uint64_t poly[2] = {0xbeac0467eba5facbULL, 0xd86b048b86aa9922ULL};
+    HState acc = {0, 0};
+    for (int i = 0; i < 2; ++i)
+        for (int b = 0; b < 64; ++b) {
+            if (poly[i] & (1ULL << b)) {
+                acc.s0 ^= s.s0;
+                acc.s1 ^= s.s1;
+            }
+            h_next(s);
+        }
+    return acc;
+}
+
+inline HState h_apply(const HState *cols, HState v)
+{
+    HState acc = {0, 0};
+    for (int b = 0; b < 64; ++b)
+        if ((v.s0 >> b) & 1) {
+            acc.s0 ^= cols[b].s0;
+            acc.s1 ^= cols[b].s1;
+        }
+    for (int b = 0; b < 64; ++b)
+        if ((v.s1 >> b) & 1) {
+            acc.s0 ^= cols[64 + b].s0;
+            acc.s1 ^= cols[64 + b].s1;
+        }
+    return acc;
+}
+
+// pows[k*128 + b] = J^(2^k) e_b.  The jump is linear over GF(2), so J's columns are the jumps of
+// the unit vectors and each further power is the previous matrix applied to its own columns.
+const std::vector<HState> &jump_powers()
+{
+    static std::vector<HState> pows;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        pows.resize(64 * 128);
+        for (int b = 0; b < 128; ++b) {
+            HState e = {b < 64 ? (1ULL << b) : 0, b >= 64 ? (1ULL << (b - 64)) : 0};
+            pows[b] = h_jump(e);
+        }
+        for (int k = 1; k < 64; ++k)
+            for (int b = 0; b < 128; ++b) pows[k * 128 + b] = h_apply(&pows[(k - 1) * 128], pows[(k - 1) * 128 + b]);
+    });
+    return pows;
+}
+
+// numba/cuda/random.py:46-69
+inline uint64_t splitmix64(uint64_t seed)
+{
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+std::mutex g_pow_mu;
+ulonglong2 *g_dev_pows[64] = {nullptr};  // per device ordinal
+
+int device_jump_powers(int device, ulonglong2 **out)
+{
+    if (device < 0 || device >= 64) return fail(DSB_EINVAL, "device ordinal out of range");
+    std::lock_guard<std::mutex> lk(g_pow_mu);
+    if (!g_dev_pows[device]) {
+        const std::vector<HState> &p = jump_powers();
+        ulonglong2 *d = nullptr;
+        DSB_CUDA(cudaMalloc(&d, p.size() * sizeof(HState)));
+        DSB_CUDA(cudaMemcpy(d, p.data(), p.size() * sizeof(HState), cudaMemcpyHostToDevice));
+        g_dev_pows[device] = d;
+    }
+    *out = g_dev_pows[device];
+    return DSB_OK;
+}
+
+int launch_rng_init(int device, uint64_t seed, uint64_t start, int64_t n, ulonglong2 *d_out, cudaStream_t st)
+{
+    if (n <= 0) return DSB_OK;
+    ulonglong2 *pows = nullptr;
+    int rc = device_jump_powers(device, &pows);
+    if (rc) return rc;
+    int64_t blocks = (n + 255) / 256;
+    dsb::rng_init_kernel<<<(unsigned)blocks, 256, 0, st>>>(splitmix64(seed), start, (long long)n, pows, d_out);
+    DSB_CUDA(cudaGetLastError());
+    return DSB_OK;
+}
+
+// ------------------------------------------------------------- mesh upload
+
+struct MeshBuffers {
+    double *tri9 = nullptr;
+    int *tri_idx = nullptr;
+    int2 *cell_rng = nullptr;
+    double *xs = nullptr, *ys = nullptr, *zs = nullptr;
+    dsb::MeshDev dev{};
+    void release()
+    {
+        cudaFree(tri9);
+        cudaFree(tri_idx);
+        cudaFree(cell_rng);
+        cudaFree(xs);
+        cudaFree(ys);
+        cudaFree(zs);
+        *this = MeshBuffers();
+    }
+};
+
+// Re-lays the reference's mesh arrays out for the kernels: int64 indices become int32, and the
+// three vertex gathers per test (simulations.py:100-118) become one 72-byte record per triangle
+// holding A, B-A, C-A.
+int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
+{
+    if (!m.vertices || !m.faces || !m.xs || !m.ys || !m.zs || !m.subvoxel_indices ||
+        (m.n_triangle_indices > 0 && !m.triangle_indices))
+        return fail(DSB_EINVAL, "mesh: null array");
+    if (m.n_faces <= 0 || m.n_vertices <= 0 || m.n_faces > 0x7fffffffLL || m.n_triangle_indices > 0x7fffffffLL)
+        return fail(DSB_EINVAL, "mesh: sizes out of range");
+    for (int k = 0; k < 3; ++k)
+        if (m.n_sv[k] <= 0 || m.n_sv[k] > 1 << 20) return fail(DSB_EINVAL, "mesh: n_sv out of range");
+    const int64_t n_cells = m.n_sv[0] * m.n_sv[1] * m.n_sv[2];
+    if (n_cells > 0x7fffffffLL) return fail(DSB_EINVAL, "mesh: too many subvoxels");
+    std::vector<double> tri9((size_t)m.n_faces * 9);
+    for (int64_t f = 0; f < m.n_faces; ++f) {
+        const int64_t *idx = m.faces + 3 * f;
+        for (int c = 0; c < 3; ++c)
+            if (idx[c] < 0 || idx[c] >= m.n_vertices) return fail(DSB_EINVAL, "mesh: face index out of range");
+        const double *A = m.vertices + 3 * idx[0], *B = m.vertices + 3 * idx[1], *C = m.vertices + 3 * idx[2];
+        double *o = &tri9[(size_t)f * 9];
+        for (int c = 0; c < 3; ++c) {
+            o[c] = A[c];
+            o[3 + c] = B[c] - A[c];
+            o[6 + c] = C[c] - A[c];
+        }
+    }
+    std::vector<int> tri_idx((size_t)m.n_triangle_indices);
+    for (int64_t i = 0; i < m.n_triangle_indices; ++i) {
+        if (m.triangle_indices[i] < 0 || m.triangle_indices[i] >= m.n_faces)
+            return fail(DSB_EINVAL, "mesh: triangle index out of range");
+        tri_idx[(size_t)i] = (int)m.triangle_indices[i];
+    }
+    std::vector<int2> cells((size_t)n_cells);
+    for (int64_t c = 0; c < n_cells; ++c) {
+        int64_t a = m.subvoxel_indices[2 * c], b = m.subvoxel_indices[2 * c + 1];
+        if (a < 0 || b < a || b > m.n_triangle_indices) return fail(DSB_EINVAL, "mesh: subvoxel range out of bounds");
+        cells[(size_t)c] = make_int2((int)a, (int)b);
+    }
+    DSB_CUDA(cudaMalloc(&mb.tri9, tri9.size() * sizeof(double)));
+    DSB_CUDA(cudaMalloc(&mb.tri_idx, (tri_idx.size() + 1) * sizeof(int)));
+    DSB_CUDA(cudaMalloc(&mb.cell_rng, cells.size() * sizeof(int2)));
+    DSB_CUDA(cudaMalloc(&mb.xs, (m.n_sv[0] + 1) * sizeof(double)));
+    DSB_CUDA(cudaMalloc(&mb.ys, (m.n_sv[1] + 1) * sizeof(double)));
+    DSB_CUDA(cudaMalloc(&mb.zs, (m.n_sv[2] + 1) * sizeof(double)));
+    DSB_CUDA(cudaMemcpy(mb.tri9, tri9.data(), tri9.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (!tri_idx.empty())
+        DSB_CUDA(cudaMemcpy(mb.tri_idx, tri_idx.data(), tri_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaMemcpy(mb.cell_rng, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaMemcpy(mb.xs, m.xs, (m.n_sv[0] + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaMemcpy(mb.ys, m.ys, (m.n_sv[1] + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaMemcpy(mb.zs, m.zs, (m.n_sv[2] + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    dsb::MeshDev &d = mb.dev;
+    d.tri9 = mb.tri9;
+    d.tri_idx = mb.tri_idx;
+    d.cell_rng = mb.cell_rng;
+    d.xs = mb.xs;
+    d.ys = mb.ys;
+    d.zs = mb.zs;
+    d.len_xs = (int)m.n_sv[0] + 1;
+    d.len_ys = (int)m.n_sv[1] + 1;
+    d.len_zs = (int)m.n_sv[2] + 1;
+    d.nsv1 = (int)m.n_sv[1];
+    d.nsv2 = (int)m.n_sv[2];
+    d.inv_hx = m.n_sv[0] / (m.xs[m.n_sv[0]] - m.xs[0]);
+    d.inv_hy = m.n_sv[1] / (m.ys[m.n_sv[1]] - m.ys[0]);
+    d.inv_hz = m.n_sv[2] / (m.zs[m.n_sv[2]] - m.zs[0]);
+    d.perm_prob = m.perm_prob;
+    return DSB_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------- the handle
+
+struct dsb_sim {
+    dsb_params prm{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double *d_grad = nullptr, *d_pos = nullptr, *d_phases = nullptr, *d_partials = nullptr, *d_signal = nullptr;
+    unsigned long long *d_rng = nullptr, *d_rng0 = nullptr;
+    unsigned char *d_exc = nullptr;
+    MeshBuffers mesh;
+    int64_t t_cur = -1;  // -1: positions not set
+    int grid = 0;
+    double kernel_ms = 0.0;
+    int64_t n_launches = 0;
+    bool finalized = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+namespace {
+
+template <int SUB>
+void launch_walk(const dsb::KParams &kp, int grid, cudaStream_t st)
+{
+    switch (kp.n_meas <= dsb::kMaxRegMeas ? kp.n_meas : 0) {
+    case 1: dsb::walk_kernel<SUB, 1><<<grid, dsb::kBlock, 0, st>>>(kp); break;
+    case 2: dsb::walk_kernel<SUB, 2><<<grid, dsb::kBlock, 0, st>>>(kp); break;
+    case 3: dsb::walk_kernel<SUB, 3><<<grid, dsb::kBlock, 0, st>>>(kp); break;
+    case 4: dsb::walk_kernel<SUB, 4><<<grid, dsb::kBlock, 0, st>>>(kp); break;
+    default: dsb::walk_kernel<SUB, 0><<<grid, dsb::kBlock, 0, st>>>(kp); break;
+    }
+}
+
+int check_params(const dsb_params *p, const double *gradient)
+{
+    if (!p || !gradient) return fail(DSB_EINVAL, "null params or gradient");
+    if (p->substrate < DSB_FREE || p->substrate > DSB_MESH) return fail(DSB_EINVAL, "unknown substrate");
+    if (p->n_walkers <= 0) return fail(DSB_EINVAL, "n_walkers must be positive");
+    if (p->n_walkers > (int64_t)0x7fffffff * dsb::kBlock) return fail(DSB_EINVAL, "n_walkers too large for one shard");
+    if (p->n_meas <= 0 || p->n_meas > 0x3fffffff) return fail(DSB_EINVAL, "n_meas out of range");
+    if (p->n_t <= 0 || p->n_t > 0x7fffffff) return fail(DSB_EINVAL, "n_t out of range");
+    if (p->walker_offset < 0) return fail(DSB_EINVAL, "walker_offset must be non-negative");
+    if (p->max_iter < 1) return fail(DSB_EINVAL, "max_iter must be >= 1");
+    if (!(p->step_l > 0) || !(p->dt > 0)) return fail(DSB_EINVAL, "step_l and dt must be positive");
+    if ((p->substrate == DSB_SPHERE || p->substrate == DSB_CYLINDER) && !(p->radius > 0))
+        return fail(DSB_EINVAL, "radius must be positive");
+    return DSB_OK;
+}
+
+int sync_stats(dsb_sim *s)
+{
+    for (auto &pr : s->pending) {
+        float ms = 0.f;
+        DSB_CUDA(cudaEventSynchronize(pr.second));
+        DSB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        s->kernel_ms += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    s->pending.clear();
+    return DSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *dsb_last_error(void) { return g_err.c_str(); }
+const char *dsb_version(void) { return "disimpy_b200 0.1 (sm_100a)"; }
+
+int dsb_device_count(int32_t *count)
+{
+    if (!count) return fail(DSB_EINVAL, "null argument");
+    *count = 0;
+    int n = 0;
+    DSB_CUDA(cudaGetDeviceCount(&n));
+    *count = n;
+    return DSB_OK;
+}
+
+int dsb_destroy(dsb_sim *s)
+{
+    if (!s) return DSB_OK;
+    cudaSetDevice(s->prm.device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto &pr : s->pending) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    cudaFree(s->d_grad);
+    cudaFree(s->d_pos);
+    cudaFree(s->d_phases);
+    cudaFree(s->d_partials);
+    cudaFree(s->d_signal);
+    cudaFree(s->d_rng);
+    cudaFree(s->d_rng0);
+    cudaFree(s->d_exc);
+    s->mesh.release();
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return DSB_OK;
+}
+
+int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
+{
+    if (!out) return fail(DSB_EINVAL, "null out pointer");
+    *out = nullptr;
+    int rc = check_params(params, gradient);
+    if (rc) return rc;
+    int n_dev = 0;
+    DSB_CUDA(cudaGetDeviceCount(&n_dev));
+    if (params->device < 0 || params->device >= n_dev) return fail(DSB_EINVAL, "no such CUDA device");
+    DSB_CUDA(cudaSetDevice(params->device));
+    dsb_sim *s = new (std::nothrow) dsb_sim();
+    if (!s) return fail(DSB_ENOMEM, "host allocation failed");
+    s->prm = *params;
+    const int64_t N = params->n_walkers, M = params->n_meas, T = params->n_t;
+    s->grid = (int)((N + dsb::kBlock - 1) / dsb::kBlock);
+#define DSB_TRY(expr)                 \
+    do {                              \
+        cudaError_t e_ = (expr);      \
+        if (e_ != cudaSuccess) {      \
+            std::string msg = std::string(#expr) + ": " + cudaGetErrorString(e_); \
+            int code = e_ == cudaErrorMemoryAllocation ? DSB_ENOMEM : DSB_ECUDA;  \
+            cudaGetLastError();       \
+            dsb_destroy(s);           \
+            return fail(code, msg);   \
+        }                             \
+    } while (0)
+    DSB_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    DSB_TRY(cudaMalloc(&s->d_grad, sizeof(double) * 3 * M * T));
+    DSB_TRY(cudaMalloc(&s->d_pos, sizeof(double) * 3 * N));
+    DSB_TRY(cudaMalloc(&s->d_phases, sizeof(double) * M * N));
+    DSB_TRY(cudaMalloc(&s->d_partials, sizeof(double) * (M + 1) * s->grid));
+    DSB_TRY(cudaMalloc(&s->d_signal, sizeof(double) * (M + 1)));
+    DSB_TRY(cudaMalloc(&s->d_rng, sizeof(unsigned long long) * 2 * N));
+    DSB_TRY(cudaMalloc(&s->d_rng0, sizeof(unsigned long long) * 2 * N));
+    DSB_TRY(cudaMalloc(&s->d_exc, N));
+    DSB_TRY(cudaMemcpyAsync(s->d_grad, gradient, sizeof(double) * 3 * M * T, cudaMemcpyHostToDevice, s->stream));
+#undef DSB_TRY
+    if (params->substrate == DSB_MESH) {
+        rc = upload_mesh(params->mesh, s->mesh);
+        if (rc) {
+            std::string keep = g_err;
+            dsb_destroy(s);
+            return fail(rc, keep);
+        }
+    }
+    s->prm.mesh = dsb_mesh{};  // host pointers are not kept
+    rc = launch_rng_init(params->device, params->seed, (uint64_t)params->walker_offset, N,
+                         reinterpret_cast<ulonglong2 *>(s->d_rng0), s->stream);
+    if (rc) {
+        std::string keep = g_err;
+        dsb_destroy(s);
+        return fail(rc, keep);
+    }
+    *out = s;
+    return DSB_OK;
+}
+
+static int rewind_sim(dsb_sim *s)
+{
+    const int64_t N = s->prm.n_walkers;
+    DSB_CUDA(cudaMemcpyAsync(s->d_rng, s->d_rng0, sizeof(unsigned long long) * 2 * N, cudaMemcpyDeviceToDevice, s->stream));
+    DSB_CUDA(cudaMemsetAsync(s->d_exc, 0, N, s->stream));
+    for (auto &pr : s->pending) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    s->pending.clear();
+    s->t_cur = 0;
+    s->kernel_ms = 0.0;
+    s->n_launches = 0;
+    s->finalized = false;
+    return DSB_OK;
+}
+
+int dsb_set_positions(dsb_sim *s, const double *positions)
+{
+    if (!s || !positions) return fail(DSB_EINVAL, "null argument");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    DSB_CUDA(cudaMemcpyAsync(s->d_pos, positions, sizeof(double) * 3 * s->prm.n_walkers, cudaMemcpyHostToDevice, s->stream));
+    return rewind_sim(s);
+}
+
+int dsb_set_positions_dev(dsb_sim *s, const double *positions_dev)
+{
+    if (!s || !positions_dev) return fail(DSB_EINVAL, "null argument");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    DSB_CUDA(cudaMemcpyAsync(s->d_pos, positions_dev, sizeof(double) * 3 * s->prm.n_walkers, cudaMemcpyDeviceToDevice, s->stream));
+    return rewind_sim(s);
+}
+
+int dsb_run(dsb_sim *s, int64_t t0, int64_t t1)
+{
+    if (!s) return fail(DSB_EINVAL, "null handle");
+    if (s->t_cur < 0) return fail(DSB_ESTATE, "dsb_run before dsb_set_positions");
+    if (t0 != s->t_cur || t1 <= t0 || t1 > s->prm.n_t) return fail(DSB_EINVAL, "bad step range");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    const dsb_params &P = s->prm;
+    dsb::KParams kp{};
+    kp.n_walkers = P.n_walkers;
+    kp.n_meas = (int)P.n_meas;
+    kp.n_t = (int)P.n_t;
+    kp.t0 = (int)t0;
+    kp.t1 = (int)t1;
+    kp.finalize = t1 == P.n_t;
+    kp.max_iter = P.max_iter;
+    kp.step_l = P.step_l;
+    kp.gamma_dt = P.dt * 267.513e6;  // dt * GAMMA (gradients.py:13), one rounding like the reference
+    kp.eps = P.epsilon;
+    kp.radius = P.radius;
+    memcpy(kp.R, P.R, sizeof kp.R);
+    memcpy(kp.Rinv, P.R_inv, sizeof kp.Rinv);
+    memcpy(kp.ax, P.semiaxes, sizeof kp.ax);
+    kp.grad = s->d_grad;
+    kp.pos = s->d_pos;
+    kp.rng = s->d_rng;
+    kp.phases = s->d_phases;
+    kp.iter_exc = s->d_exc;
+    kp.partials = s->d_partials;
+    kp.mesh = s->mesh.dev;
+    cudaEvent_t e0, e1;
+    DSB_CUDA(cudaEventCreate(&e0));
+    DSB_CUDA(cudaEventCreate(&e1));
+    DSB_CUDA(cudaEventRecord(e0, s->stream));
+    switch (P.substrate) {
+    case DSB_FREE: launch_walk<0>(kp, s->grid, s->stream); break;
+    case DSB_SPHERE: launch_walk<1>(kp, s->grid, s->stream); break;
+    case DSB_CYLINDER: launch_walk<2>(kp, s->grid, s->stream); break;
+    case DSB_ELLIPSOID: launch_walk<3>(kp, s->grid, s->stream); break;
+    default: launch_walk<4>(kp, s->grid, s->stream); break;
+    }
+    DSB_CUDA(cudaGetLastError());
+    s->n_launches += 1;
+    if (kp.finalize) {
+        dsb::reduce_partials_kernel<<<(unsigned)(P.n_meas + 1), 256, 0, s->stream>>>(s->d_partials, s->grid, s->d_signal);
+        DSB_CUDA(cudaGetLastError());
+        s->n_launches += 1;
+        s->finalized = true;
+    }
+    DSB_CUDA(cudaEventRecord(e1, s->stream));
+    s->pending.emplace_back(e0, e1);
+    s->t_cur = t1;
+    return DSB_OK;
+}
+
+int dsb_sync(dsb_sim *s)
+{
+    if (!s) return fail(DSB_EINVAL, "null handle");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    DSB_CUDA(cudaStreamSynchronize(s->stream));
+    return DSB_OK;
+}
+
+int dsb_get_signal(dsb_sim *s, double *signal, int64_t *n_valid)
+{
+    if (!s || !signal) return fail(DSB_EINVAL, "null argument");
+    if (!s->finalized) return fail(DSB_ESTATE, "signal is available after the last time step only");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    std::vector<double> h((size_t)s->prm.n_meas + 1);
+    DSB_CUDA(cudaMemcpyAsync(h.data(), s->d_signal, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    DSB_CUDA(cudaStreamSynchronize(s->stream));
+    memcpy(signal, h.data(), sizeof(double) * (size_t)s->prm.n_meas);
+    if (n_valid) *n_valid = (int64_t)llround(h.back());
+    return DSB_OK;
+}
+
+#define DSB_GETTER(name, type, member, count)                                                             \
+    int name(dsb_sim *s, type *dst)                                                                       \
+    {                                                                                                     \
+        if (!s || !dst) return fail(DSB_EINVAL, "null argument");                                         \
+        if (s->t_cur < 0) return fail(DSB_ESTATE, "no walker state yet");                                 \
+        DSB_CUDA(cudaSetDevice(s->prm.device));                                                           \
+        DSB_CUDA(cudaMemcpyAsync(dst, s->member, sizeof(type) * (size_t)(count), cudaMemcpyDeviceToHost, s->stream)); \
+        DSB_CUDA(cudaStreamSynchronize(s->stream));                                                       \
+        return DSB_OK;                                                                                    \
+    }
+
+DSB_GETTER(dsb_get_positions, double, d_pos, 3 * s->prm.n_walkers)
+DSB_GETTER(dsb_get_phases, double, d_phases, s->prm.n_meas *s->prm.n_walkers)
+DSB_GETTER(dsb_get_iter_exc, uint8_t, d_exc, s->prm.n_walkers)
+DSB_GETTER(dsb_get_rng_states, uint64_t, d_rng, 2 * s->prm.n_walkers)
+
+int dsb_get_run_stats(dsb_sim *s, double *kernel_ms, int64_t *n_launches)
+{
+    if (!s) return fail(DSB_EINVAL, "null handle");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    int rc = sync_stats(s);
+    if (rc) return rc;
+    if (kernel_ms) *kernel_ms = s->kernel_ms;
+    if (n_launches) *n_launches = s->n_launches;
+    return DSB_OK;
+}
+
+void *dsb_stream(dsb_sim *s) { return s ? (void *)s->stream : nullptr; }
+double *dsb_signal_dev(dsb_sim *s) { return s ? s->d_signal : nullptr; }
+
+int dsb_simulate(const dsb_params *params, const double *gradient, const double *positions_in,
+                 double *signal_out, int64_t *n_valid_out, double *positions_out, double *phases_out,
+                 uint8_t *iter_exc_out)
+{
+    if (!positions_in || !signal_out) return fail(DSB_EINVAL, "null argument");
+    dsb_sim *s = nullptr;
+    int rc = dsb_create(params, gradient, &s);
+    if (rc) return rc;
+    rc = dsb_set_positions(s, positions_in);
+    if (!rc) rc = dsb_run(s, 0, params->n_t);
+    if (!rc) rc = dsb_get_signal(s, signal_out, n_valid_out);
+    if (!rc && positions_out) rc = dsb_get_positions(s, positions_out);
+    if (!rc && phases_out) rc = dsb_get_phases(s, phases_out);
+    if (!rc && iter_exc_out) rc = dsb_get_iter_exc(s, iter_exc_out);
+    std::string keep = g_err;
+    dsb_destroy(s);
+    if (rc) g_err = keep;
+    return rc;
+}
+
+int dsb_rng_states(int32_t device, uint64_t seed, uint64_t subsequence_start, int64_t n, uint64_t *states)
+{
+    if (n < 0 || (n > 0 && !states)) return fail(DSB_EINVAL, "bad arguments");
+    if (n == 0) return DSB_OK;
+    DSB_CUDA(cudaSetDevice(device));
+    ulonglong2 *d = nullptr;
+    DSB_CUDA(cudaMalloc(&d, sizeof(ulonglong2) * (size_t)n));
+    int rc = launch_rng_init(device, seed, subsequence_start, n, d, 0);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy(states, d, sizeof(ulonglong2) * (size_t)n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(DSB_ECUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int dsb_fill_mesh(int32_t device, const dsb_mesh *mesh, const double *voxel_size, int intra, uint64_t seed,
+                  int64_t n_points, int64_t cuda_bs, double *points)
+{
+    if (!mesh || !voxel_size || !points || n_points <= 0 || cuda_bs <= 0) return fail(DSB_EINVAL, "bad arguments");
+    DSB_CUDA(cudaSetDevice(device));
+    MeshBuffers mb;
+    int rc = upload_mesh(*mesh, mb);
+    if (rc) {
+        mb.release();
+        return rc;
+    }
+    const int64_t n_states = (n_points + cuda_bs - 1) / cuda_bs * cuda_bs;
+    ulonglong2 *d_rng = nullptr;
+    double *d_pts = nullptr;
+    int *d_count = nullptr;
+    cudaError_t e = cudaMalloc(&d_rng, sizeof(ulonglong2) * (size_t)n_states);
+    if (e == cudaSuccess) e = cudaMalloc(&d_pts, sizeof(double) * 3 * (size_t)n_points);
+    if (e == cudaSuccess) e = cudaMalloc(&d_count, sizeof(int));
+    if (e != cudaSuccess) rc = fail(DSB_ENOMEM, cudaGetErrorString(e));
+    if (!rc) rc = launch_rng_init(device, seed, 0, n_states, d_rng, 0);
+    std::vector<double> round_pts((size_t)n_points * 3);
+    int64_t have = 0;
+    const double inf = INFINITY;
+    // The reference launches one round per host-loop iteration, keeps the accepted points of
+    // every round in thread order and stops once it has enough (simulations.py:554-579).
+    for (int round = 0; !rc && have < n_points; ++round) {
+        if (round > 100000) {
+            rc = fail(DSB_ESTATE, "fill_mesh: no acceptable points (is the surface closed?)");
+            break;
+        }
+        dsb::fill_mesh_kernel<<<(unsigned)((n_points + 127) / 128), 128>>>(mb.dev, voxel_size[0], voxel_size[1],
+                                                                            voxel_size[2], intra, (long long)n_points,
+                                                                            d_rng, d_pts);
+        e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = cudaMemcpy(round_pts.data(), d_pts, sizeof(double) * 3 * (size_t)n_points, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            rc = fail(DSB_ECUDA, cudaGetErrorString(e));
+            break;
+        }
+        for (int64_t i = 0; i < n_points && have < n_points; ++i)
+            if (round_pts[3 * i] != inf) {
+                memcpy(points + 3 * have, &round_pts[3 * i], 3 * sizeof(double));
+                ++have;
+            }
+    }
+    cudaFree(d_rng);
+    cudaFree(d_pts);
+    cudaFree(d_count);
+    mb.release();
+    return rc;
+}
+
+}  // extern "C"

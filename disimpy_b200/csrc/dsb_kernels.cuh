@@ -1,0 +1,441 @@
+// dsb_kernels.cuh -- the walk kernels.  One thread owns one walker for the whole launch: RNG
+// state, FP64 position and (for up to DSB_MAX_REG_MEAS measurements) the phase accumulators
+// stay in registers across all time steps of the launch; HBM is touched once at entry and once
+// at exit.  Replaces the reference's one-launch-per-time-step kernels
+// (disimpy/simulations.py:682-1013) and the host-side signal reduction (:1413-1421).
+#pragma once
+#include "dsb_geom.cuh"
+
+namespace dsb {
+
+constexpr int kBlock = 128;          // threads (= walkers) per CTA
+constexpr int kMaxRegMeas = 4;       // measurements whose phase lives in registers
+constexpr int kTimeChunk = 8;        // steps buffered per phase pass when n_meas is larger
+
+struct MeshDev {
+    const double *tri9;     // (n_faces, 9): A, B-A, C-A
+    const int *tri_idx;     // (K,) triangle ids, cell after cell (reference order)
+    const int2 *cell_rng;   // (n_cells,) [begin, end) into tri_idx
+    const double *xs, *ys, *zs;
+    int len_xs, len_ys, len_zs;
+    int nsv1, nsv2;
+    double inv_hx, inv_hy, inv_hz;  // guesses only, never part of a result
+    double perm_prob;
+};
+
+struct KParams {
+    long long n_walkers;
+    int n_meas, n_t;
+    int t0, t1;
+    int finalize;  // t1 == n_t: also emit per-block sum(cos phase) partials
+    long long max_iter;
+    double step_l, gamma_dt, eps, radius;
+    double R[9], Rinv[9], ax[3];
+    const double *grad;         // (n_meas, n_t, 3)
+    double *pos;                // (n_walkers, 3)
+    unsigned long long *rng;    // (n_walkers, 2)
+    double *phases;             // (n_meas, n_walkers)
+    unsigned char *iter_exc;    // (n_walkers,)
+    double *partials;           // (n_meas + 1, gridDim.x)
+    MeshDev mesh;
+};
+
+// ---------------------------------------------------------------- one time step, per substrate
+
+template <int SUB>
+__device__ __forceinline__ bool walker_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab);
+
+// simulations.py:682-702
+template <>
+__device__ __forceinline__ bool walker_step<0>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab)
+{
+    Vec3 s = random_step(rng, tab);
+    pos.x = fma_(s.x, p.step_l, pos.x);
+    pos.y = fma_(s.y, p.step_l, pos.y);
+    pos.z = fma_(s.z, p.step_l, pos.z);
+    return false;
+}
+
+// simulations.py:705-756
+template <>
+__device__ __forceinline__ bool walker_step<1>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab)
+{
+    Vec3 s = random_step(rng, tab);
+    double step_l = p.step_l;
+    long long iter = 0;
+    bool check = true;
+    while (check && step_l > 0 && iter < p.max_iter) {
+        ++iter;
+        double d = line_sphere(pos, s, p.radius);
+        if (d > 0 && d < step_l) {
+            Vec3 n;
+            n.x = -fma_(d, s.x, pos.x);
+            n.y = -fma_(d, s.y, pos.y);
+            n.z = -fma_(d, s.z, pos.z);
+            n = normalize3(n);
+            reflect(pos, s, d, n, p.eps);
+            step_l = sub_(step_l, add_(d, p.eps));
+        } else {
+            check = false;
+        }
+    }
+    pos.x = fma_(step_l, s.x, pos.x);
+    pos.y = fma_(step_l, s.y, pos.y);
+    pos.z = fma_(step_l, s.z, pos.z);
+    return iter >= p.max_iter;
+}
+
+// simulations.py:759-816.  The position is rotated into the cylinder frame and back every
+// step, like the reference (the rounding of the round trip is part of the trajectory).
+template <>
+__device__ __forceinline__ bool walker_step<2>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab)
+{
+    Vec3 s = random_step(rng, tab);
+    Vec3 r0 = matvec3(p.R, pos);
+    double step_l = p.step_l;
+    long long iter = 0;
+    bool check = true;
+    while (check && step_l > 0 && iter < p.max_iter) {
+        ++iter;
+        double d = line_circle(r0, s, p.radius);
+        if (d > 0 && d < step_l) {
+            double X1 = fma_(d, s.y, r0.y), X2 = fma_(d, s.z, r0.z);
+            double len = sqrt_(fma_(X2, X2, fma_(X1, X1, 0.0)));
+            Vec3 n;
+            n.x = div_(0.0, len);
+            n.y = div_(-X1, len);
+            n.z = div_(-X2, len);
+            reflect(r0, s, d, n, p.eps);
+            step_l = sub_(step_l, add_(d, p.eps));
+        } else {
+            check = false;
+        }
+    }
+    s = matvec3(p.Rinv, s);
+    r0 = matvec3(p.Rinv, r0);
+    pos.x = fma_(step_l, s.x, r0.x);
+    pos.y = fma_(step_l, s.y, r0.y);
+    pos.z = fma_(step_l, s.z, r0.z);
+    return iter >= p.max_iter;
+}
+
+// simulations.py:819-875
+template <>
+__device__ __forceinline__ bool walker_step<3>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab)
+{
+    Vec3 s = random_step(rng, tab);
+    Vec3 r0 = matvec3(p.R, pos);
+    double step_l = p.step_l;
+    long long iter = 0;
+    bool check = true;
+    while (check && step_l > 0 && iter < p.max_iter) {
+        ++iter;
+        double d = line_ellipsoid(r0, s, p.ax);
+        if (d > 0 && d < step_l) {
+            Vec3 n;
+            n.x = div_(-fma_(d, s.x, r0.x), mul_(p.ax[0], p.ax[0]));
+            n.y = div_(-fma_(d, s.y, r0.y), mul_(p.ax[1], p.ax[1]));
+            n.z = div_(-fma_(d, s.z, r0.z), mul_(p.ax[2], p.ax[2]));
+            n = normalize3(n);
+            reflect(r0, s, d, n, p.eps);
+            step_l = sub_(step_l, add_(d, p.eps));
+        } else {
+            check = false;
+        }
+    }
+    s = matvec3(p.Rinv, s);
+    r0 = matvec3(p.Rinv, r0);
+    pos.x = fma_(step_l, s.x, r0.x);
+    pos.y = fma_(step_l, s.y, r0.y);
+    pos.z = fma_(step_l, s.z, r0.z);
+    return iter >= p.max_iter;
+}
+
+__device__ __forceinline__ Tri load_tri(const double *tri9, int id)
+{
+    const double *q = tri9 + 9ll * id;
+    Tri t;
+    t.A.x = __ldg(q + 0); t.A.y = __ldg(q + 1); t.A.z = __ldg(q + 2);
+    t.E1.x = __ldg(q + 3); t.E1.y = __ldg(q + 4); t.E1.z = __ldg(q + 5);
+    t.E2.x = __ldg(q + 6); t.E2.y = __ldg(q + 7); t.E2.z = __ldg(q + 8);
+    return t;
+}
+
+// floor(i / n) and i - floor(i/n)*n for a cell index outside [0, n): the reference does this
+// in FP64 (simulations.py:940-943); for |i| < 2^40 the integer result is identical.
+__device__ __forceinline__ void wrap_cell(long long i, int n, int &wrapped, double &shift_n)
+{
+    if (i < 0 || i > n - 1) {
+        long long q = i / n;
+        if (i % n != 0 && i < 0) --q;
+        wrapped = (int)(i - q * n);
+        shift_n = (double)q;
+    } else {
+        wrapped = (int)i;
+        shift_n = 0.0;
+    }
+}
+
+// simulations.py:878-1013
+template <>
+__device__ __forceinline__ bool walker_step<4>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab)
+{
+    const MeshDev &g = p.mesh;
+    Vec3 s = random_step(rng, tab);
+    double step_l = p.step_l;
+    long long iter = 0;
+    bool check = true;
+    int closest = 0;
+    while (check && step_l > 0 && iter < p.max_iter) {
+        ++iter;
+        double min_d = __longlong_as_double(0x7FF0000000000000LL);
+        // end point of the remaining segment: x uses a separately rounded product, y and z are
+        // fused (that is how the reference's kernel was compiled)
+        double ex = add_(pos.x, mul_(step_l, s.x));
+        double ey = fma_(step_l, s.y, pos.y);
+        double ez = fma_(step_l, s.z, pos.z);
+        long long lx = ll_overlap_periodic(g.xs, g.len_xs, pos.x, ex, g.inv_hx);
+        long long ly = ll_overlap_periodic(g.ys, g.len_ys, pos.y, ey, g.inv_hy);
+        long long lz = ll_overlap_periodic(g.zs, g.len_zs, pos.z, ez, g.inv_hz);
+        long long ux = ul_overlap_periodic(g.xs, g.len_xs, pos.x, ex, g.inv_hx);
+        long long uy = ul_overlap_periodic(g.ys, g.len_ys, pos.y, ey, g.inv_hy);
+        long long uz = ul_overlap_periodic(g.zs, g.len_zs, pos.z, ez, g.inv_hz);
+        for (long long xi = lx; xi < ux; ++xi) {
+            int cx;
+            double snx;
+            wrap_cell(xi, g.len_xs - 1, cx, snx);
+            double tx = sub_(pos.x, snx == 0.0 ? 0.0 : mul_(snx, g.xs[g.len_xs - 1]));
+            for (long long yi = ly; yi < uy; ++yi) {
+                int cy;
+                double sny;
+                wrap_cell(yi, g.len_ys - 1, cy, sny);
+                double ty = sub_(pos.y, sny == 0.0 ? 0.0 : mul_(sny, g.ys[g.len_ys - 1]));
+                for (long long zi = lz; zi < uz; ++zi) {
+                    int cz;
+                    double snz;
+                    wrap_cell(zi, g.len_zs - 1, cz, snz);
+                    double tz = sub_(pos.z, snz == 0.0 ? 0.0 : mul_(snz, g.zs[g.len_zs - 1]));
+                    Vec3 tr0 = {tx, ty, tz};
+                    int2 rng_c = __ldg(g.cell_rng + ((long long)cx * g.nsv1 + cy) * g.nsv2 + cz);
+                    for (int i = rng_c.x; i < rng_c.y; ++i) {
+                        int id = __ldg(g.tri_idx + i);
+                        Tri tr = load_tri(g.tri9, id);
+                        double d = ray_triangle(tr, tr0, s);
+                        if (d > 0 && d < min_d) {
+                            closest = id;
+                            min_d = d;
+                        }
+                    }
+                }
+            }
+        }
+        if (min_d > step_l) {
+            check = false;
+        } else {
+            double u = u01_f64(rng_next(rng));
+            Tri tr = load_tri(g.tri9, closest);
+            Vec3 n = triangle_normal(tr);
+            if (g.perm_prob < u)
+                reflect(pos, s, min_d, n, p.eps);
+            else
+                cross_membrane(pos, s, min_d, n, p.eps);
+            step_l = sub_(step_l, min_d);
+        }
+    }
+    pos.x = fma_(step_l, s.x, pos.x);
+    pos.y = fma_(step_l, s.y, pos.y);
+    pos.z = fma_(step_l, s.z, pos.z);
+    return iter >= p.max_iter;
+}
+
+// ---------------------------------------------------------------- block reduction of the signal
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// phase(m) -> per-block sum of cos(phase) over walkers with a clear iter_exc flag, written to
+// partials[m * gridDim.x + blockIdx.x]; row n_meas receives the number of such walkers.
+// Fixed summation tree: results do not depend on scheduling.
+template <typename PhaseFn>
+__device__ __forceinline__ void block_signal(const KParams &p, bool valid, PhaseFn phase_of)
+{
+    __shared__ double s_part[kBlock / 32][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows = p.n_meas + 1;
+    for (int m0 = 0; m0 < rows; m0 += 32) {
+        int mt = min(32, rows - m0);
+        for (int j = 0; j < mt; ++j) {
+            int m = m0 + j;
+            double v = 0.0;
+            if (valid) v = (m < p.n_meas) ? cos(phase_of(m)) : 1.0;
+            v = warp_sum(v);
+            if (lane == 0) s_part[warp][j] = v;
+        }
+        __syncthreads();
+        if (warp == 0 && lane < mt) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; ++w) acc += s_part[w][lane];
+            p.partials[(long long)(m0 + lane) * gridDim.x + blockIdx.x] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- the walk kernel
+
+// MR > 0: n_meas == MR phases in registers.  MR == 0: any n_meas; positions of kTimeChunk steps
+// are buffered in registers, then each measurement's phase makes one round trip through its
+// (coalesced, L2-resident) row of `phases` per chunk instead of one per step.
+template <int SUB, int MR>
+__global__ void __launch_bounds__(kBlock) walk_kernel(const __grid_constant__ KParams p)
+{
+    __shared__ double s_tab[16];
+    if (threadIdx.x < 16) s_tab[threadIdx.x] = __longlong_as_double((long long)c_sincos_tab[threadIdx.x]);
+    __syncthreads();
+
+    const long long w = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const bool active = w < p.n_walkers;
+    const long long N = p.n_walkers;
+    Vec3 pos = {0.0, 0.0, 0.0};
+    Rng rng = {1ull, 1ull};
+    bool exc = false;
+    if (active) {
+        pos.x = p.pos[3 * w];
+        pos.y = p.pos[3 * w + 1];
+        pos.z = p.pos[3 * w + 2];
+        ulonglong2 st = reinterpret_cast<const ulonglong2 *>(p.rng)[w];
+        rng.s0 = st.x;
+        rng.s1 = st.y;
+    }
+
+    if constexpr (MR > 0) {
+        double ph[MR];
+#pragma unroll
+        for (int m = 0; m < MR; ++m) ph[m] = (active && p.t0 > 0) ? p.phases[(long long)m * N + w] : 0.0;
+        if (active) {
+            for (int t = p.t0; t < p.t1; ++t) {
+                exc |= walker_step<SUB>(pos, rng, p, s_tab);
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    const double *g = p.grad + ((long long)m * p.n_t + t) * 3;
+                    double gx = __ldg(g), gy = __ldg(g + 1), gz = __ldg(g + 2);
+                    ph[m] = fma_(p.gamma_dt, fma_(gz, pos.z, fma_(gx, pos.x, mul_(gy, pos.y))), ph[m]);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < MR; ++m) p.phases[(long long)m * N + w] = ph[m];
+        }
+        if (active) {
+            if (exc) p.iter_exc[w] = 1;
+            else exc = p.iter_exc[w] != 0;
+        }
+        if (p.finalize)
+            block_signal(p, active && !exc, [&](int m) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < MR; ++k)
+                    if (k == m) v = ph[k];
+                return v;
+            });
+    } else {
+        if (active) {
+            if (p.t0 == 0)
+                for (int m = 0; m < p.n_meas; ++m) p.phases[(long long)m * N + w] = 0.0;
+            Vec3 buf[kTimeChunk];
+            for (int t = p.t0; t < p.t1; t += kTimeChunk) {
+                const int cnt = min(kTimeChunk, p.t1 - t);
+#pragma unroll
+                for (int k = 0; k < kTimeChunk; ++k)
+                    if (k < cnt) {
+                        exc |= walker_step<SUB>(pos, rng, p, s_tab);
+                        buf[k] = pos;
+                    }
+                for (int m = 0; m < p.n_meas; ++m) {
+                    double *row = p.phases + (long long)m * N + w;
+                    double a = *row;
+                    const double *g = p.grad + ((long long)m * p.n_t + t) * 3;
+#pragma unroll
+                    for (int k = 0; k < kTimeChunk; ++k)
+                        if (k < cnt) {
+                            double gx = __ldg(g + 3 * k), gy = __ldg(g + 3 * k + 1), gz = __ldg(g + 3 * k + 2);
+                            a = fma_(p.gamma_dt, fma_(gz, buf[k].z, fma_(gx, buf[k].x, mul_(gy, buf[k].y))), a);
+                        }
+                    *row = a;
+                }
+            }
+            if (exc) p.iter_exc[w] = 1;
+            else exc = p.iter_exc[w] != 0;
+        }
+        if (p.finalize)
+            block_signal(p, active && !exc, [&](int m) { return p.phases[(long long)m * N + w]; });
+    }
+
+    if (active) {
+        p.pos[3 * w] = pos.x;
+        p.pos[3 * w + 1] = pos.y;
+        p.pos[3 * w + 2] = pos.z;
+        reinterpret_cast<ulonglong2 *>(p.rng)[w] = make_ulonglong2(rng.s0, rng.s1);
+    }
+}
+
+// Sums the per-block partials of one measurement (or of the valid-walker count) in a fixed
+// order: thread j takes blocks j, j + 256, ...; then a shared-memory tree.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double *partials, int n_blocks, double *out)
+{
+    __shared__ double s[256];
+    const double *row = partials + (long long)blockIdx.x * n_blocks;
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < n_blocks; b += 256) acc += row[b];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = s[0];
+}
+
+// ---------------------------------------------------------------- RNG state derivation
+
+// state[i] = J^(start + i) * splitmix64(seed), J = the 2^64-step jump of xoroshiro128+ as a
+// 128x128 matrix over GF(2).  pows[k] holds J^(2^k) column by column (column b = image of unit
+// vector b); applying the matrices for the set bits of the index reproduces numba's sequential
+// jump chain (numba/cuda/random.py:102-126, 225-241) without the O(N) host loop.
+__global__ void __launch_bounds__(256) rng_init_kernel(unsigned long long z, unsigned long long start,
+                                                       long long n, const ulonglong2 *pows,
+                                                       ulonglong2 *out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long idx = start + (unsigned long long)i;
+    unsigned long long s0 = z, s1 = z;
+    for (int k = 0; k < 64 && (idx >> k) != 0; ++k) {
+        if (((idx >> k) & 1ull) == 0) continue;
+        const ulonglong2 *col = pows + 128 * k;
+        unsigned long long a0 = 0, a1 = 0;
+#pragma unroll 8
+        for (int b = 0; b < 64; ++b) {
+            ulonglong2 c = __ldg(col + b);
+            unsigned long long mask = 0ull - ((s0 >> b) & 1ull);
+            a0 ^= c.x & mask;
+            a1 ^= c.y & mask;
+        }
+#pragma unroll 8
+        for (int b = 0; b < 64; ++b) {
+            ulonglong2 c = __ldg(col + 64 + b);
+            unsigned long long mask = 0ull - ((s1 >> b) & 1ull);
+            a0 ^= c.x & mask;
+            a1 ^= c.y & mask;
+        }
+        s0 = a0;
+        s1 = a1;
+    }
+    out[i] = make_ulonglong2(s0, s1);
+}
+
+}  // namespace dsb

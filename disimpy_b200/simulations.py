@@ -1,0 +1,453 @@
+"""``simulation()``: drop-in for disimpy.simulations.simulation (simulations.py:1051-1429).
+
+Same signature, validation, prints, warnings, seeding side effects and return values as
+the reference.  What changes is everything between "inputs are validated" and "signal is
+returned": instead of one Numba launch + stream sync per time step, the walk, the phase
+accumulation and the sum of cos(phase) run inside libdisimpy_b200.so (hand-written sm_100a
+CUDA behind the C ABI in include/disimpy_b200.h).  There is no CPU fallback.
+
+Multi-GPU: when ``torch.distributed`` is initialised, every rank simulates the contiguous
+walker range ``[rank*N/W, (rank+1)*N/W)`` with RNG subsequence offset = first global walker
+index, and the signal (+ valid-walker count) is summed with one all-reduce; results do not
+depend on the number of ranks (up to floating-point summation order of the signal).
+"""
+
+import ctypes
+import math
+import os
+import sys
+import warnings
+
+import numpy as np
+
+from . import _lib, substrates, utils
+from .gradients import GAMMA  # noqa: F401  (same module-level name as the reference)
+
+
+# ----------------------------------------------------------------------------------------
+# host-side initial positions (simulations.py:346-418): sequential rejection sampling from
+# the MT19937 stream seeded with ``seed`` -- Numba's CPU generator after _set_seed(seed) is
+# np.random.RandomState(seed) -- vectorised in blocks, same acceptance order.
+
+def _rejection_sample(rs, n, scale, dim, accept):
+    out = np.zeros((0, dim))
+    while len(out) < n:
+        k = max(4096, int((n - len(out)) * 2.3))
+        cand = (rs.random_sample((k, dim)) - 0.5) * 2 * scale
+        out = np.concatenate([out, cand[accept(cand)]])
+    return out[:n]
+
+
+def _fill_circle(n, radius, rs=None):
+    """n points uniform in a disc (simulations.py:353-366)."""
+    rs = np.random.RandomState() if rs is None else rs
+    return _rejection_sample(rs, n, radius, 2, lambda p: np.sqrt((p * p).sum(axis=1)) < radius)
+
+
+def _fill_sphere(n, radius, rs=None):
+    """n points uniform in a ball (simulations.py:369-382)."""
+    rs = np.random.RandomState() if rs is None else rs
+    return _rejection_sample(rs, n, radius, 3, lambda p: np.sqrt((p * p).sum(axis=1)) < radius)
+
+
+def _fill_ellipsoid(n, semiaxes, rs=None):
+    """n points uniform in an axis-aligned ellipsoid (simulations.py:385-399)."""
+    rs = np.random.RandomState() if rs is None else rs
+
+    def inside(p):
+        q = (p / semiaxes) ** 2
+        return q[:, 0] + q[:, 1] + q[:, 2] < 1
+    return _rejection_sample(rs, n, semiaxes, 3, inside)
+
+
+def _initial_positions_cylinder(n_walkers, radius, R, rs=None):
+    """Points in the cross-section of a cylinder, rotated to the lab frame by R
+    (simulations.py:402-409)."""
+    positions = np.zeros((n_walkers, 3))
+    positions[:, 1:3] = _fill_circle(n_walkers, radius, rs)
+    return np.matmul(R, positions.T).T
+
+
+def _initial_positions_ellipsoid(n_walkers, semiaxes, R, rs=None):
+    """Points in an ellipsoid, rotated to the lab frame by R (simulations.py:412-418)."""
+    return np.matmul(R, _fill_ellipsoid(n_walkers, semiaxes, rs).T).T
+
+
+def _fill_mesh(n_points, substrate, intra, seed, cuda_bs=128):
+    """Uniform points inside / outside the closed surface of a mesh substrate
+    (simulations.py:505-579), sampled on the GPU with the reference's RNG streams and accept
+    order.  Non-periodic substrates are sampled against the mesh without its 12 wall
+    triangles, with the reference's index bookkeeping (simulations.py:531-546)."""
+    if substrate.periodic:
+        m, keep = _lib.mesh_struct(substrate)
+    else:
+        n_faces = len(substrate.faces) - 12
+        tri = np.asarray(substrate.triangle_indices)
+        svi = np.array(substrate.subvoxel_indices, dtype=np.int64)
+        is_wall = tri >= n_faces
+        # the reference shifts both ends of a cell range by the number of removed entries
+        # that precede the range's END, then clamps at 0
+        removed_before = np.concatenate([[0], np.cumsum(is_wall)])
+        svi = svi - removed_before[svi[:, 1]][:, None]
+        svi[svi < 0] = 0
+        m, keep = _lib.mesh_struct(substrate, vertices=substrate.vertices[0:-8],
+                                   faces=substrate.faces[0:-12], triangle_indices=tri[~is_wall],
+                                   subvoxel_indices=svi)
+    voxel = _lib.f64(substrate.voxel_size)
+    points = np.zeros((n_points, 3))
+    _lib.check(_lib.lib().dsb_fill_mesh(_device(), ctypes.byref(m), _lib.ptr(voxel),
+                                        1 if intra else 0, seed, n_points, cuda_bs,
+                                        _lib.ptr(points)), "dsb_fill_mesh")
+    return points
+
+
+# ----------------------------------------------------------------------------------------
+
+def add_noise_to_data(data, sigma, seed=None):
+    """Add Rician noise to data (simulations.py:1016-1040)."""
+    if seed:
+        np.random.seed(seed)
+    real = np.random.normal(size=data.shape, scale=sigma, loc=0)
+    imag = np.random.normal(size=data.shape, scale=sigma, loc=0)
+    return np.abs(data + real + 1j * imag)
+
+
+def _write_traj(traj, mode, positions):
+    """One line per time point: x y z of walker 1, walker 2, ... (simulations.py:1043-1048)."""
+    with open(traj, mode) as f:
+        f.write("".join(str(v) + " " for v in positions.ravel()))
+        f.write("\n")
+
+
+def _device():
+    """CUDA device ordinal of this process: DISIMPY_B200_DEVICE, else LOCAL_RANK, else 0."""
+    for name in ("DISIMPY_B200_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(name, "") != "":
+            return int(os.environ[name])
+    return 0
+
+
+def _require_gpu():
+    count = ctypes.c_int32(0)
+    try:
+        rc = _lib.lib().dsb_device_count(ctypes.byref(count))
+    except ImportError:
+        raise
+    if rc != 0 or count.value < 1:
+        raise Exception(
+            "disimpy_b200 was unable to detect a CUDA GPU. To run the simulation, a B200 "
+            "(sm_100a) and a working CUDA driver are required; there is no CPU fallback.")
+
+
+def _dist():
+    """(rank, world_size, torch.distributed or None)"""
+    try:
+        import torch.distributed as dist
+    except Exception:  # pragma: no cover - torch is part of the image
+        return 0, 1, None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size(), dist
+    return 0, 1, None
+
+
+def shard_range(n_walkers, rank, world_size):
+    """Contiguous global walker range of a rank."""
+    return n_walkers * rank // world_size, n_walkers * (rank + 1) // world_size
+
+
+def make_params(substrate, n_walkers, walker_offset, gradient, dt, step_l, seed, max_iter,
+                epsilon, device=None):
+    """Fill the C ABI's dsb_params for one shard; returns (params, keep_alive)."""
+    p = _lib.DsbParams()
+    p.substrate = _lib.SUBSTRATE_CODE[substrate.type]
+    p.device = _device() if device is None else device
+    p.n_walkers = n_walkers
+    p.walker_offset = walker_offset
+    p.n_meas, p.n_t = gradient.shape[0], gradient.shape[1]
+    p.seed = seed
+    p.max_iter = max_iter
+    p.step_l, p.dt, p.epsilon = float(step_l), float(dt), float(epsilon)
+    keep = []
+    if substrate.type in ("sphere", "cylinder"):
+        p.radius = substrate.radius
+    if substrate.type == "cylinder":
+        # lab -> cylinder frame and back (simulations.py:1221-1222)
+        R = utils.vec2vec_rotmat(substrate.orientation, np.array([1.0, 0, 0]))
+        R_inv = np.linalg.inv(R)
+        p.R[:] = list(_lib.f64(R).ravel())
+        p.R_inv[:] = list(_lib.f64(R_inv).ravel())
+    if substrate.type == "ellipsoid":
+        # substrate.R is ellipsoid -> lab (simulations.py:1297-1299)
+        p.semiaxes[:] = list(substrate.semiaxes)
+        p.R_inv[:] = list(_lib.f64(substrate.R).ravel())
+        p.R[:] = list(_lib.f64(np.linalg.inv(substrate.R)).ravel())
+    if substrate.type == "mesh":
+        p.mesh, keep = _lib.mesh_struct(substrate)
+    return p, keep
+
+
+class Walk:
+    """Thin RAII wrapper of one ``dsb_sim`` handle (one shard on one GPU)."""
+
+    def __init__(self, params, gradient):
+        self.params = params
+        self.n_walkers, self.n_meas, self.n_t = params.n_walkers, params.n_meas, params.n_t
+        self._h = ctypes.c_void_p()
+        self._L = _lib.lib()
+        g = _lib.f64(gradient)
+        _lib.check(self._L.dsb_create(ctypes.byref(params), _lib.ptr(g), ctypes.byref(self._h)),
+                   "dsb_create")
+
+    def set_positions(self, positions):
+        pos = _lib.f64(positions)
+        _lib.check(self._L.dsb_set_positions(self._h, _lib.ptr(pos)), "dsb_set_positions")
+
+    def set_positions_dev(self, dev_ptr):
+        _lib.check(self._L.dsb_set_positions_dev(self._h, ctypes.c_void_p(dev_ptr)),
+                   "dsb_set_positions_dev")
+
+    def run(self, t0=0, t1=None):
+        _lib.check(self._L.dsb_run(self._h, t0, self.n_t if t1 is None else t1), "dsb_run")
+
+    def sync(self):
+        _lib.check(self._L.dsb_sync(self._h), "dsb_sync")
+
+    def signal(self):
+        sig = np.zeros(self.n_meas)
+        n_valid = ctypes.c_int64(0)
+        _lib.check(self._L.dsb_get_signal(self._h, _lib.ptr(sig), ctypes.byref(n_valid)),
+                   "dsb_get_signal")
+        return sig, n_valid.value
+
+    def positions(self):
+        out = np.zeros((self.n_walkers, 3))
+        _lib.check(self._L.dsb_get_positions(self._h, _lib.ptr(out)), "dsb_get_positions")
+        return out
+
+    def phases(self):
+        out = np.zeros((self.n_meas, self.n_walkers))
+        _lib.check(self._L.dsb_get_phases(self._h, _lib.ptr(out)), "dsb_get_phases")
+        return out
+
+    def iter_exc(self):
+        out = np.zeros(self.n_walkers, dtype=np.uint8)
+        _lib.check(self._L.dsb_get_iter_exc(self._h, _lib.ptr(out)), "dsb_get_iter_exc")
+        return out.astype(bool)
+
+    def rng_states(self):
+        out = np.zeros((self.n_walkers, 2), dtype=np.uint64)
+        _lib.check(self._L.dsb_get_rng_states(self._h, _lib.ptr(out)), "dsb_get_rng_states")
+        return out
+
+    def run_stats(self):
+        ms = ctypes.c_double(0)
+        n = ctypes.c_int64(0)
+        _lib.check(self._L.dsb_get_run_stats(self._h, ctypes.byref(ms), ctypes.byref(n)),
+                   "dsb_get_run_stats")
+        return ms.value, n.value
+
+    def close(self):
+        if self._h:
+            self._L.dsb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def rng_states(seed, n, subsequence_start=0, device=None):
+    """(n, 2) uint64 xoroshiro128+ states, what numba's create_xoroshiro128p_states(n, seed,
+    subsequence_start) holds (numba/cuda/random.py:225-292), derived on the GPU."""
+    out = np.zeros((n, 2), dtype=np.uint64)
+    _lib.check(_lib.lib().dsb_rng_states(_device() if device is None else device, seed,
+                                         subsequence_start, n, _lib.ptr(out)), "dsb_rng_states")
+    return out
+
+
+def simulation(
+    n_walkers,
+    diffusivity,
+    gradient,
+    dt,
+    substrate,
+    seed=123,
+    traj=None,
+    final_pos=False,
+    all_signals=False,
+    quiet=False,
+    cuda_bs=128,
+    max_iter=int(1e3),
+    epsilon=1e-13,
+):
+    """Simulate a diffusion-weighted MR experiment and generate signal.
+
+    Parameters and return values are those of the reference (simulations.py:1066-1113):
+    ``gradient`` has shape (n_measurements, n_time_points, 3) in T/m, ``dt`` is the time step
+    in s, ``substrate`` comes from :mod:`disimpy_b200.substrates`.  Returns ``signals``
+    (n_measurements,) -- or the per-walker signals (n_measurements, n_walkers) when
+    ``all_signals`` -- and additionally the final positions (n_walkers, 3) when ``final_pos``.
+    ``cuda_bs`` is accepted for compatibility; it only fixes the number of RNG streams of the
+    'intra'/'extra' mesh sampler like it does in the reference.
+    """
+    _require_gpu()
+
+    if not isinstance(n_walkers, int) or n_walkers <= 0:
+        raise ValueError("Incorrect value (%s) for n_walkers" % n_walkers)
+    if not isinstance(diffusivity, float) or diffusivity <= 0:
+        raise ValueError("Incorrect value (%s) for diffusivity" % diffusivity)
+    if (not isinstance(gradient, np.ndarray) or gradient.ndim != 3 or gradient.shape[2] != 3
+            or not np.issubdtype(gradient.dtype, np.floating)):
+        raise ValueError("Incorrect value (%s) for gradient" % gradient)
+    if not isinstance(dt, float) or dt <= 0:
+        raise ValueError("Incorrect value (%s) for dt" % dt)
+    if not isinstance(substrate, substrates._Substrate):
+        raise ValueError("Incorrect value (%s) for substrate" % substrate)
+    if not isinstance(seed, int) or seed < 0:
+        raise ValueError("Incorrect value (%s) for seed" % seed)
+    if traj:
+        if not isinstance(traj, str):
+            raise ValueError("Incorrect value (%s) for traj" % traj)
+    if not isinstance(quiet, bool):
+        raise ValueError("Incorrect value (%s) for quiet" % quiet)
+    if not isinstance(cuda_bs, int) or cuda_bs <= 0:
+        raise ValueError("Incorrect value (%s) for cuda_bs" % cuda_bs)
+    if not isinstance(max_iter, int) or max_iter < 1:
+        raise ValueError("Incorrect value (%s) for max_iter" % max_iter)
+    if substrate.type not in _lib.SUBSTRATE_CODE:
+        raise ValueError("Incorrect value (%s) for substrate" % substrate)
+
+    n_t = gradient.shape[1]
+    if not quiet:
+        print("Starting simulation")
+        if traj:
+            print("The trajectories file will be up to %s GB" % (n_t * n_walkers * 3 * 25 / 1e9))
+
+    # Same seeding side effect as the reference (simulations.py:1169-1170): NumPy's global
+    # generator is reseeded; the host samplers use an MT19937 stream with the same seed.
+    np.random.seed(seed)
+    rs = np.random.RandomState(seed)
+    step_l = np.sqrt(6 * diffusivity * dt)
+
+    if not quiet:
+        print("Number of random walkers = %s" % n_walkers)
+        print("Number of steps = %s" % n_t)
+        print("Step length = %s m" % step_l)
+        print("Step duration = %s s" % dt)
+
+    if substrate.type == "free":
+        positions = np.zeros((n_walkers, 3))
+    elif substrate.type == "cylinder":
+        R = utils.vec2vec_rotmat(substrate.orientation, np.array([1.0, 0, 0]))
+        positions = _initial_positions_cylinder(n_walkers, substrate.radius, np.linalg.inv(R), rs)
+    elif substrate.type == "sphere":
+        positions = _fill_sphere(n_walkers, substrate.radius, rs)
+    elif substrate.type == "ellipsoid":
+        positions = _initial_positions_ellipsoid(n_walkers, substrate.semiaxes, substrate.R, rs)
+    else:
+        if isinstance(substrate.init_pos, np.ndarray):
+            if n_walkers != substrate.init_pos.shape[0]:
+                raise ValueError("n_walkers must be equal to the number of initial positions")
+            positions = substrate.init_pos
+        else:
+            if not quiet:
+                print("Calculating initial positions")
+            if substrate.init_pos == "uniform":
+                positions = np.random.random((n_walkers, 3)) * substrate.voxel_size
+            elif substrate.init_pos == "intra":
+                positions = _fill_mesh(n_walkers, substrate, True, seed, cuda_bs)
+            else:
+                positions = _fill_mesh(n_walkers, substrate, False, seed, cuda_bs)
+            if not quiet:
+                print("Finished calculating initial positions")
+
+    rank, world, dist = _dist()
+    lo, hi = shard_range(n_walkers, rank, world)
+    if traj and rank == 0:
+        _write_traj(traj, "w", positions)
+
+    params, keep = make_params(substrate, hi - lo, lo, gradient, dt, step_l, seed, max_iter,
+                               epsilon)
+    walk = Walk(params, gradient)
+    try:
+        walk.set_positions(positions[lo:hi])
+        if traj:
+            for t in range(n_t):
+                walk.run(t, t + 1)
+                step_pos = _gather_rows(walk.positions(), n_walkers, lo, hi, dist)
+                if rank == 0:
+                    _write_traj(traj, "a", step_pos)
+                if not quiet:
+                    sys.stdout.write(f"\r{np.round((t / n_t) * 100, 1)}%")
+                    sys.stdout.flush()
+        elif quiet:
+            walk.run(0, n_t)
+        else:  # a handful of launches so that progress can be shown
+            edges = np.unique(np.linspace(0, n_t, min(n_t, 20) + 1).astype(int))
+            for t0, t1 in zip(edges[:-1], edges[1:]):
+                sys.stdout.write(f"\r{np.round((t0 / n_t) * 100, 1)}%")
+                sys.stdout.flush()
+                walk.run(int(t0), int(t1))
+                walk.sync()
+
+        # The signal kernel also counts the walkers whose iter_exc flag is clear, so the
+        # per-walker flags only travel to the host when something was flagged (or when the
+        # caller asked for per-walker output).
+        if all_signals:
+            iter_exc = walk.iter_exc()
+            n_flagged = int(iter_exc.sum())
+        else:
+            signals, n_valid = walk.signal()
+            n_flagged = (hi - lo) - n_valid
+            iter_exc = None
+        if dist is not None:
+            n_flagged = int(round(_allreduce_sum(np.array([float(n_flagged)]), dist)[0]))
+        if n_flagged > 0:
+            if iter_exc is None:
+                iter_exc = walk.iter_exc()
+            iter_exc_all = _gather_rows(iter_exc, n_walkers, lo, hi, dist)
+            warnings.warn(
+                "Maximum number of iterations was exceeded in the intersection "
+                + "check algorithm for walkers %s" % np.where(iter_exc_all)[0])
+
+        if all_signals:
+            phases = walk.phases()
+            phases[:, np.where(iter_exc)[0]] = np.nan
+            signals = np.real(np.exp(1j * phases))
+            signals = _gather_rows(signals.T, n_walkers, lo, hi, dist).T
+        elif dist is not None:
+            signals = _allreduce_sum(signals, dist)
+        if not quiet:
+            sys.stdout.write("\rSimulation finished\n")
+            sys.stdout.flush()
+        if final_pos:
+            final = _gather_rows(walk.positions(), n_walkers, lo, hi, dist)
+            return signals, final
+        return signals
+    finally:
+        walk.close()
+
+
+def _allreduce_sum(values, dist):
+    """Sum a small float64 vector over ranks (NCCL on the GPU when that backend is active)."""
+    import torch
+    dev = "cuda:%d" % _device() if dist.get_backend() == "nccl" else "cpu"
+    t = torch.as_tensor(np.ascontiguousarray(values), dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def _gather_rows(local, n_total, lo, hi, dist):
+    """Assemble per-walker rows from all ranks (only used for final_pos / all_signals / traj
+    / the iter_exc warning -- per-shard host gathers, no device collective)."""
+    if dist is None:
+        return local
+    import torch
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, (lo, hi, local))
+    full = np.zeros((n_total,) + local.shape[1:], dtype=local.dtype)
+    for a, b, part in out:
+        full[a:b] = part
+    return full

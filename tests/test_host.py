@@ -1,0 +1,319 @@
+"""CPU-only tests: the C ABI library loads and exports what include/disimpy_b200.h declares,
+host-side logic (validation, substrates, mesh binning, initial positions, sharding) and the
+reference's CPU-level known answers (tests/test_substrates.py, tests/test_gradients.py,
+tests/test_utils.py of the reference).  No compute call touches a GPU here."""
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, oracle_substrate, product_substrate
+
+
+def test_library_exports_every_declared_symbol():
+    from disimpy_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "disimpy_b200.h")).read()
+    declared = set(re.findall(r"\b(dsb_[a-z_0-9]+)\s*\(", header))
+    declared -= {"dsb_reset"}  # mentioned in the mapping comment only
+    L = _lib.lib()
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(L, name), "missing export %s" % name
+    assert set(_lib.EXPORTS) == declared
+    assert b"sm_100a" in L.dsb_version()
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirror of dsb_params / dsb_mesh has the C layout (checked via a tiny C program)."""
+    from disimpy_b200 import _lib
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "disimpy_b200.h"
+    int main(void) {
+        printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(dsb_params), sizeof(dsb_mesh),
+               offsetof(dsb_params, seed), offsetof(dsb_params, R), offsetof(dsb_params, mesh),
+               offsetof(dsb_mesh, n_sv), offsetof(dsb_mesh, perm_prob));
+        return 0;
+    }'''
+    exe = os.path.join(ROOT, "oracle", "_build", "layout_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe],
+                   input=src.encode(), check=True)
+    got = [int(v) for v in subprocess.run([exe], capture_output=True, check=True).stdout.split()]
+    P, M = _lib.DsbParams, _lib.DsbMesh
+    assert got == [ctypes.sizeof(P), ctypes.sizeof(M), P.seed.offset, P.R.offset, P.mesh.offset,
+                   M.n_sv.offset, M.perm_prob.offset]
+
+
+def test_no_gpu_fails_loudly():
+    """Without a CUDA device simulation() raises instead of computing anything on the CPU."""
+    from disimpy_b200 import _lib, gradients, simulations, substrates
+    count = ctypes.c_int32(0)
+    rc = _lib.lib().dsb_device_count(ctypes.byref(count))
+    if rc == 0 and count.value > 0:
+        pytest.skip("a GPU is present")
+    g, dt = gradients.pgse(5e-3, 20e-3, 10, [1e9], [[1.0, 0, 0]])
+    with pytest.raises(Exception, match="unable to detect a CUDA GPU"):
+        simulations.simulation(10, 2e-9, g, dt, substrates.free(), quiet=True)
+    with pytest.raises(_lib.DsbError):
+        simulations.rng_states(1, 4)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "disimpy_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "meshgen.py", f
+
+
+# ------------------------------------------------------------------ substrates
+
+def test_substrate_validation():
+    from disimpy_b200 import substrates
+    assert substrates.free().type == "free"
+    s = substrates.sphere(1e-6)
+    assert (s.type, s.radius) == ("sphere", 1e-6)
+    for bad in (1, -1.0, "r", 0.0):
+        with pytest.raises(ValueError):
+            substrates.sphere(bad)
+    c = substrates.cylinder(2e-6, np.array([0.0, 0.0, 2.0]))
+    assert np.array_equal(c.orientation, [0, 0, 1.0])
+    for bad_o in ([0, 0, 1.0], np.array([0, 0, 1]), np.zeros(2)):
+        with pytest.raises(ValueError):
+            substrates.cylinder(2e-6, bad_o)
+    e = substrates.ellipsoid(np.array([1e-6, 2e-6, 3e-6]))
+    assert np.array_equal(e.R, np.eye(3))
+    with pytest.raises(ValueError):
+        substrates.ellipsoid(np.array([1e-6, 2e-6, 3e-6]), 2 * np.eye(3))
+    with pytest.raises(ValueError):
+        substrates.ellipsoid(np.array([1, 2, 3]))
+
+
+def test_mesh_validation_and_layout():
+    from disimpy_b200 import meshgen, substrates
+    v, f = meshgen.icosphere(1e-6, 1)
+    with pytest.raises(ValueError):
+        substrates.mesh(v.astype(int), f, True, quiet=True)
+    with pytest.raises(ValueError):
+        substrates.mesh(v, f.astype(float), True, quiet=True)
+    with pytest.raises(ValueError):
+        substrates.mesh(v, f, 1, quiet=True)
+    with pytest.raises(ValueError):
+        substrates.mesh(v, f, True, init_pos="inside", quiet=True)
+    with pytest.raises(ValueError):
+        substrates.mesh(v, f, True, perm_prob=2.0, quiet=True)
+    with pytest.raises(ValueError):
+        substrates.mesh(v, f, True, n_sv=np.array([5.0, 5, 5]), quiet=True)
+    pad = np.array([1e-7, 2e-7, 3e-7])
+    s = substrates.mesh(v, f, False, padding=pad, n_sv=np.array([4, 5, 6]), quiet=True)
+    assert np.allclose(s.vertices[:-8].min(axis=0), pad)
+    assert np.allclose(s.voxel_size, s.vertices[:-8].max(axis=0) + pad)
+    assert len(s.faces) == len(f) + 12 and len(s.vertices) == len(v) + 8
+    assert np.array_equal(s.vertices[-8], [0, 0, 0]) and np.array_equal(s.vertices[-5], s.voxel_size)
+    assert s.subvoxel_indices.shape == (120, 2) and s.subvoxel_indices[-1, 1] == len(s.triangle_indices)
+    assert len(s.xs) == 5 and len(s.ys) == 6 and len(s.zs) == 7
+    p = substrates.mesh(v, f, True, quiet=True)
+    assert len(p.faces) == len(f)
+
+
+def test_reference_unit_known_answers():
+    """tests/test_substrates.py:293-363 of the reference."""
+    from disimpy_b200 import substrates
+    tri = np.array([[0.5, 0.7, 0.3], [0.9, 0.5, 0.2], [0.6, 0.9, 0.8]])
+    assert not substrates._triangle_box_overlap(tri, np.array([[0.1, 0.3, 0.1], [0.4, 0.7, 0.5]]))
+    tri = np.array([[0.4, 0.7, 0.2], [0.9, 0.5, 0.2], [0.6, 0.9, 0.2]])
+    assert not substrates._triangle_box_overlap(tri, np.array([[0.4, 0.4, 0.3], [0.5, 0.8, 0.6]]))
+    tri = np.array([[0.63149023, 0.44235872, 0.77212144], [0.25125724, 0.00087658, 0.66026559],
+                    [0.8319006, 0.52731735, 0.22859846]])
+    box = np.array([[0.33109806, 0.16637023, 0.91545459], [0.79806038, 0.83915475, 0.38118002]])
+    assert substrates._triangle_box_overlap(tri, box)
+    xs = np.arange(11)
+    assert substrates._interval_sv_overlap(xs, 0, 0) == (0, 1)
+    assert substrates._interval_sv_overlap(xs, 0, 1.5) == (0, 2)
+    assert substrates._interval_sv_overlap(xs, 9.5, 1.5) == (1, 10)
+    assert substrates._interval_sv_overlap(xs, -1.1, 0.5) == (0, 1)
+    assert substrates._interval_sv_overlap(xs, 9.5, 11.5) == (9, 10)
+
+
+def test_mesh_subdivision_reference_golden():
+    """tests/test_substrates.py:366-400: sphere_mesh.pkl, n_sv = [2, 5, 10]."""
+    from disimpy_b200 import substrates
+    rm = load_golden("ref_meshes")
+    s = substrates.mesh(rm["sphere_mesh_vertices"], rm["sphere_mesh_faces"], True,
+                        n_sv=np.array([2, 5, 10]), quiet=True)
+    assert np.array_equal(s.triangle_indices, rm["desired_triangle_indices"])
+    assert np.array_equal(s.subvoxel_indices, rm["desired_subvoxel_indices"])
+
+
+@pytest.mark.parametrize("name", ["mesh_tubes_uniform", "mesh_sphere_np_uniform",
+                                  "mesh_sphere_p_intra", "mesh_tubes_perm"])
+def test_mesh_substrate_equals_reference_arrays(name):
+    """Substrate arrays the unmodified reference built for the same input mesh."""
+    g = load_golden(name)
+    s = product_substrate(name, g)
+    for k in ("vertices", "faces", "voxel_size", "xs", "ys", "zs", "triangle_indices",
+              "subvoxel_indices"):
+        assert np.array_equal(getattr(s, k), g["sub_" + k]), k
+
+
+def test_mesh_subdivision_threaded_equals_serial():
+    """> 2048 faces takes the multi-threaded path; the cell lists must stay face-ascending."""
+    from disimpy_b200 import meshgen, substrates
+    v, f, pad, _ = meshgen.tube_lattice(3, 3, 2e-6, 5e-6, 8e-6, 32, 6)
+    s = substrates.mesh(v, f, True, padding=pad, n_sv=np.array([9, 9, 5]), quiet=True)
+    assert len(f) > 2048
+    for a, b in s.subvoxel_indices:
+        cell = s.triangle_indices[a:b]
+        assert np.all(np.diff(cell) > 0)
+    # every listed pair really overlaps, and the brute-force count agrees on a sample of cells
+    rs = np.random.RandomState(0)
+    for c in rs.choice(len(s.subvoxel_indices), 12, replace=False):
+        x, rem = divmod(c, 9 * 5)
+        y, z = divmod(rem, 5)
+        box = np.array([[s.xs[x], s.ys[y], s.zs[z]], [s.xs[x + 1], s.ys[y + 1], s.zs[z + 1]]])
+        hits = [i for i in range(len(f)) if substrates._triangle_box_overlap(s.vertices[s.faces[i]], box)]
+        a, b = s.subvoxel_indices[c]
+        assert list(s.triangle_indices[a:b]) == hits
+
+
+# ------------------------------------------------------------------ host math
+
+def test_vec2vec_rotmat():
+    from disimpy_b200 import utils
+    rs = np.random.RandomState(123)
+    for _ in range(200):
+        v, k = rs.random_sample(3) - 0.5, rs.random_sample(3) - 0.5
+        R = utils.vec2vec_rotmat(v, k)
+        assert np.allclose(R @ (v / np.linalg.norm(v)), k / np.linalg.norm(k))
+        assert np.isclose(np.linalg.det(R), 1)
+    assert np.array_equal(utils.vec2vec_rotmat(np.array([1.0, 0, 0]), np.array([2.0, 0, 0])), np.eye(3))
+    assert np.array_equal(utils.vec2vec_rotmat(np.array([1.0, 0, 0]), np.array([-1.0, 0, 0])), -np.eye(3))
+
+
+def test_gradients_known_answers():
+    """tests/test_gradients.py:20-111 of the reference."""
+    from disimpy_b200 import gradients
+    T = 80e-3
+    g = np.zeros((1, 1000, 3))
+    g[0, 1:201, 0] = 0.1
+    g[0, -201:-1, 0] = -0.1
+    dt = T / (g.shape[1] - 1)
+    assert np.allclose(gradients.calc_b(g, dt), 1.07507347e10, rtol=1e-7)
+    g2, dt2 = gradients.interpolate_gradient(g, dt, 5000)
+    assert g2.shape == (1, 5000, 3) and np.isclose(dt2, T / 4999)
+    assert np.isclose(gradients.calc_b(g2, dt2) / gradients.calc_b(g, dt), 1, atol=1e-3)
+    bs = np.array([1e9, 3e9])
+    gg = gradients.set_b(np.concatenate([g2, g2]), dt2, bs)
+    assert np.allclose(gradients.calc_b(gg, dt2), bs)
+    bvecs = np.array([[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0]])
+    bvals = np.array([1e9, 2e9, 3e9])
+    p, pdt = gradients.pgse(10e-3, 40e-3, 500, bvals, bvecs)
+    assert p.shape == (3, 500, 3)
+    assert np.allclose(p.sum(axis=1), 0, atol=1e-9)
+    assert np.allclose(gradients.calc_b(p, pdt), bvals)
+    for i in range(3):
+        off = [j for j in range(3) if j != i]
+        assert np.allclose(p[i][:, off], 0)
+
+
+def test_initial_positions_match_reference_stream():
+    """Host samplers: the first accepted points of the MT19937 stream (any failure here would
+    also break every golden comparison of final positions)."""
+    from disimpy_b200 import simulations
+    from oracle import oracle as O
+    import types
+    rs = np.random.RandomState(123)
+    pts = simulations._fill_sphere(5000, 3e-6, rs)
+    assert np.all(np.linalg.norm(pts, axis=1) < 3e-6)
+    seq = np.random.RandomState(123)
+    manual = []
+    while len(manual) < 50:
+        p = (seq.random_sample(3) - 0.5) * 2 * 3e-6
+        if np.linalg.norm(p) < 3e-6:
+            manual.append(p)
+    assert np.array_equal(pts[:50], np.array(manual))
+    sub = types.SimpleNamespace(type="sphere", radius=3e-6)
+    assert np.array_equal(pts, O.initial_positions(sub, 5000, 123))
+    ax = np.array([3e-6, 2e-6, 1e-6])
+    e = simulations._fill_ellipsoid(2000, ax, np.random.RandomState(5))
+    assert np.all(((e / ax) ** 2).sum(axis=1) < 1)
+    c = simulations._fill_circle(2000, 1e-6, np.random.RandomState(5))
+    assert c.shape == (2000, 2) and np.all(np.linalg.norm(c, axis=1) < 1e-6)
+
+
+def test_simulation_argument_validation():
+    """simulations.py:1127-1153: same ValueErrors (checked before any GPU work would start)."""
+    from disimpy_b200 import _lib, gradients, simulations, substrates
+    count = ctypes.c_int32(0)
+    if _lib.lib().dsb_device_count(ctypes.byref(count)) != 0 or count.value < 1:
+        pytest.skip("validation runs after GPU detection, like the reference")
+    g, dt = gradients.pgse(5e-3, 20e-3, 10, [1e9], [[1.0, 0, 0]])
+    sub = substrates.free()
+    for kwargs in (dict(n_walkers=1.5), dict(diffusivity=2), dict(gradient=g[0]), dict(dt=1),
+                   dict(substrate="free"), dict(seed=-1), dict(traj=5), dict(quiet=1),
+                   dict(cuda_bs=0), dict(max_iter=0)):
+        args = dict(n_walkers=10, diffusivity=2e-9, gradient=g, dt=dt, substrate=sub, quiet=True)
+        args.update(kwargs)
+        with pytest.raises(ValueError):
+            simulations.simulation(**args)
+
+
+def test_shard_ranges_cover_all_walkers():
+    from disimpy_b200 import simulations
+    for n in (1, 7, 1000, 10 ** 8 + 3):
+        for w in (1, 2, 4, 8):
+            r = [simulations.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys, types
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import torch.distributed as dist
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+from disimpy_b200 import simulations
+from oracle import oracle as O
+rank, world, d = simulations._dist()
+assert world == 2 and d is not None
+n = 301
+lo, hi = simulations.shard_range(n, rank, world)
+sub = types.SimpleNamespace(type="sphere", radius=1e-6)
+rs = np.random.RandomState(3)
+grad = rs.normal(size=(3, 25, 3)) * 0.05
+pos0 = O.initial_positions(sub, n, 9)
+# each rank walks its shard with the ORACLE standing in for the GPU kernels (host logic test)
+part = O.run_walk(sub, grad, 1e-4, 2e-9, pos0[lo:hi], seed=9, walker_offset=lo)
+sig = O.signals_from_phases(part["phases"], part["iter_exc"])
+total = simulations._allreduce_sum(sig, d)
+allpos = simulations._gather_rows(part["positions"], n, lo, hi, d)
+full = O.run_walk(sub, grad, 1e-4, 2e-9, pos0, seed=9)
+assert np.array_equal(allpos, full["positions"])
+assert np.allclose(total, O.signals_from_phases(full["phases"], full["iter_exc"]), rtol=1e-13)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    """world_size 2 on CPU: shard ranges, RNG offsets, the signal all-reduce and the row gather
+    used by simulation() reproduce the single-process result."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert "rank %d ok" % r in o
