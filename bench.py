@@ -1,0 +1,322 @@
+"""bench.py -- walker-steps/s of the random-walk hot path on N B200s (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): diffusion inside a sphere of
+radius 10 um, 1e6 walkers x 1e4 time steps per GPU, one PGSE measurement (delta = 10 ms,
+DELTA = 30 ms, b = 1e9 s/m^2), D = 2e-9 m^2/s, seed 123.  One "step" of the bench = one whole
+simulation of that batch = 1e10 walker-steps per GPU (weak scaling: rank r owns the global
+walkers [r*1e6, (r+1)*1e6) with its RNG subsequence offset; the only collective is the
+all-reduce of the signal).
+
+Prints ONE JSON line.  `value` = walker-steps/s with inputs resident in HBM, timed with CUDA
+events on the library's stream around the K timed steps (max over ranks); `e2e` = the same
+through the public disimpy_b200.simulations.simulation() call with host buffers (initial
+positions sampled on the host, H2D, kernels, D2H of the signal inside the timed region).
+`--impl reference` times the CPU restatement of the reference's algorithm (oracle/, all host
+threads) on a bounded sample of the same workload.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_WALKERS = int(os.environ.get("DSB_BENCH_WALKERS", 1_000_000))
+N_T = int(os.environ.get("DSB_BENCH_NT", 10_000))
+RADIUS = 10e-6
+DIFFUSIVITY = 2e-9
+SEED = 123
+METRIC = "walker-steps/sec (sphere r=10um, 1e6 walkers x 1e4 steps per GPU)"
+UNIT = "walker-steps/s"
+
+# Algorithmic FP64 instructions per walker-step: random unit step + move 120,
+# one line-sphere distance check 25, phase update 4 per measurement.  Collisions (reflection
+# 75 + re-check 25 each) are extra work that is NOT credited here.
+FP64_PER_WALKER_STEP = 120 + 25 + 4 * 1
+# HBM bytes the walk must move per walker per launch: position in/out (48), RNG state in/out
+# (32), phase out (8), iter_exc (1)
+HBM_BYTES_PER_WALKER = 48 + 32 + 8 + 1
+
+
+def workload():
+    from disimpy_b200 import gradients, substrates
+    g, dt = gradients.pgse(10e-3, 30e-3, N_T, [1e9], [[1.0, 0.0, 0.0]])
+    return substrates.sphere(RADIUS), g, float(dt)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(sub, g, dt, seconds_target=15.0, threads=None):
+    """Oracle (CPU port of the reference's algorithm) on a bounded sample of the workload."""
+    from oracle import oracle as O
+    threads = threads or os.cpu_count() or 1
+    n_probe = 64 * threads
+    pos = O.initial_positions(sub, n_probe, SEED)
+    t0 = time.perf_counter()
+    O.run_walk(sub, g[:, :200], dt, DIFFUSIVITY, pos, seed=SEED, n_threads=threads)
+    rate = n_probe * 200 / (time.perf_counter() - t0)
+    n = int(max(threads * 8, min(N_WALKERS, rate * seconds_target / N_T)))
+    pos = O.initial_positions(sub, n, SEED)
+    t0 = time.perf_counter()
+    O.run_walk(sub, g, dt, DIFFUSIVITY, pos, seed=SEED, n_threads=threads)
+    el = time.perf_counter() - t0
+    return {"value": n * N_T / el, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d walkers x %d steps of the same workload, incl. sequential RNG-state "
+                      "init, %.1f s" % (n, N_T, el)}, n
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; the Python
+    reference itself only has a GPU path and a ~600 walker-steps/s Numba simulator)."""
+    if rank != 0:
+        return
+    sub, g, dt = workload()
+    from oracle import oracle as O
+    threads = os.cpu_count() or 1
+    base, n = cpu_baseline(sub, g, dt, seconds_target=6.0, threads=threads)
+    times = []
+    pos = O.initial_positions(sub, n, SEED)
+    for k in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.run_walk(sub, g, dt, DIFFUSIVITY, pos, seed=SEED, n_threads=threads)
+        el = time.perf_counter() - t0
+        if k >= args.warmup:
+            times.append(el)
+    ms = 1e3 * float(np.mean(times))
+    value = n * N_T / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "sphere r=10um, PGSE b=1e9 s/m^2, D=2e-9, n_t=%d; each step = a "
+                               "%d-walker sample of the 1e6-walker batch on %d host threads"
+                               % (N_T, n, threads)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d walkers x %d steps per step" % (n, N_T)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    torch.cuda.set_device(local_rank)
+    os.environ["DISIMPY_B200_DEVICE"] = str(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+
+    from disimpy_b200 import _lib, simulations
+    import ctypes
+    sub, g, dt = workload()
+    step_l = np.sqrt(6 * DIFFUSIVITY * dt)
+
+    # Global problem = world * N_WALKERS walkers; this rank's shard, resident in HBM.
+    n_global = world * N_WALKERS
+    lo, hi = simulations.shard_range(n_global, rank, world)
+    pos_all = simulations._fill_sphere(n_global, RADIUS, np.random.RandomState(SEED))
+    d_pos0 = torch.from_numpy(np.ascontiguousarray(pos_all[lo:hi])).cuda()
+    params, keep = simulations.make_params(sub, hi - lo, lo, g, dt, step_l, SEED, 1000, 1e-13,
+                                           device=local_rank)
+    walk = simulations.Walk(params, g)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    sig_buf = torch.zeros(2, dtype=torch.float64, device="cuda")
+
+    def one_step():
+        walk.set_positions_dev(d_pos0.data_ptr())
+        walk.run(0, N_T)
+        sig, n_valid = walk.signal()          # syncs the library's stream, 16 bytes D2H
+        if world > 1:
+            sig_buf.copy_(torch.tensor([sig[0], float(n_valid)], dtype=torch.float64))
+            dist.all_reduce(sig_buf)          # the one collective of the path (NCCL)
+            out = sig_buf.cpu().numpy()
+            return out[0], int(out[1])
+        return sig[0], n_valid
+
+    def barrier():
+        torch.cuda.synchronize()
+        walk.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+        flush.zero_()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    kernel_ms_total, launches = 0.0, 0
+    ev_ms_total = 0.0
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        walk.timer_start()
+        signal, n_valid = one_step()
+        ev_ms_total += walk.timer_stop()
+        ms, nl = walk.run_stats()
+        kernel_ms_total += ms
+        launches += nl
+        flush.zero_()                          # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    clocks = sampler.stop() if sampler else None
+
+    t = torch.tensor([ev_ms_total, kernel_ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ev_ms_total, kernel_ms_max = [float(v) for v in t.cpu()]
+    ms_per_step = ev_ms_total / args.steps
+    units_per_step = n_global * N_T
+    value = units_per_step / (ms_per_step * 1e-3)
+    kernel_ms = kernel_ms_max / args.steps
+
+    # roofline of the dominant kernel (walk_kernel<sphere, 1 measurement>)
+    peak = ctypes.c_double(0)
+    _lib.check(_lib.lib().dsb_measure_fp64_peak(local_rank, ctypes.byref(peak)), "fp64 peak")
+    achieved_fp64 = FP64_PER_WALKER_STEP * (hi - lo) * N_T / (kernel_ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_achieved = HBM_BYTES_PER_WALKER * (hi - lo) / (kernel_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "fp64", "achieved": achieved_fp64 / 1e12, "peak": peak.value / 1e12,
+        "unit": "T FP64-instr/s", "frac": achieved_fp64 / peak.value, "traffic": None,
+        "kernel": "walk_kernel<sphere,1>", "kernel_ms": kernel_ms,
+        "algorithmic_fp64_instr_per_walker_step": FP64_PER_WALKER_STEP,
+        "peak_source": "measured live by dsb_measure_fp64_peak (independent DFMA chains); "
+                       "MEASURED_PEAKS.json has no FP64 figure",
+        "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": hbm_peak,
+                "frac": hbm_achieved / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_walker_per_launch": HBM_BYTES_PER_WALKER},
+    }
+
+    # end to end through the public API (host buffers in, signal out), rank-local shard sizes
+    e2e = None
+    if not args.no_e2e:
+        reps = max(2, min(args.steps, 3))
+        simulations.simulation(n_global, DIFFUSIVITY, g, dt, sub, seed=SEED, quiet=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sig_e2e = simulations.simulation(n_global, DIFFUSIVITY, g, dt, sub, seed=SEED, quiet=True)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / reps
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.cpu()[0])
+        e2e = {"value": units_per_step / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int((hi - lo) * 24 + g.nbytes),
+               "d2h_bytes_per_step": 16, "ms_per_step": 1e3 * e2e_s,
+               "signal": float(np.asarray(sig_e2e)[0])}
+
+    base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base, _ = cpu_baseline(sub, g, dt)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "sphere r=10um intra-only, %d walkers x %d steps per GPU, PGSE "
+                                   "delta=10ms DELTA=30ms b=1e9 s/m^2 (1 measurement), D=2e-9 m^2/s, "
+                                   "seed 123" % (N_WALKERS, N_T),
+                       "walkers_total": n_global, "parallelism": "walker shards x%d" % world,
+                       "l2": "256 MB flush between timed iterations"},
+            "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
+            "signal": float(signal), "n_valid": int(n_valid),
+        }
+        print(json.dumps(line), flush=True)
+    walk.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

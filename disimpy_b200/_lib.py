@@ -61,7 +61,8 @@ SUBSTRATE_CODE = {"free": 0, "sphere": 1, "cylinder": 2, "ellipsoid": 3, "mesh":
 EXPORTS = [
     "dsb_create", "dsb_set_positions", "dsb_set_positions_dev", "dsb_run", "dsb_sync",
     "dsb_get_signal", "dsb_get_positions", "dsb_get_phases", "dsb_get_iter_exc",
-    "dsb_get_rng_states", "dsb_get_run_stats", "dsb_stream", "dsb_signal_dev", "dsb_destroy",
+    "dsb_get_rng_states", "dsb_get_run_stats", "dsb_timer_start", "dsb_timer_stop",
+    "dsb_measure_fp64_peak", "dsb_stream", "dsb_signal_dev", "dsb_destroy",
     "dsb_simulate", "dsb_rng_states", "dsb_fill_mesh", "dsb_mesh_subdivide",
     "dsb_mesh_subdivide_fetch", "dsb_triangle_box_overlap", "dsb_interval_sv_overlap",
     "dsb_device_count", "dsb_last_error", "dsb_version",
@@ -99,6 +100,9 @@ def lib():
         L.dsb_destroy.argtypes = [ctypes.c_void_p]
         L.dsb_get_signal.argtypes = [ctypes.c_void_p, ctypes.c_void_p, c_int64_p]
         L.dsb_get_run_stats.argtypes = [ctypes.c_void_p, c_double_p, c_int64_p]
+        L.dsb_timer_start.argtypes = [ctypes.c_void_p]
+        L.dsb_timer_stop.argtypes = [ctypes.c_void_p, c_double_p]
+        L.dsb_measure_fp64_peak.argtypes = [ctypes.c_int32, c_double_p]
         L.dsb_simulate.argtypes = [ctypes.POINTER(DsbParams)] + [ctypes.c_void_p] * 3 + [
             c_int64_p] + [ctypes.c_void_p] * 3
         L.dsb_rng_states.argtypes = [ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64,

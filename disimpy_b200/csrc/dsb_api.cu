@@ -244,6 +244,7 @@ struct dsb_sim {
     int64_t n_launches = 0;
     bool finalized = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
 };
 
 namespace {
@@ -316,6 +317,8 @@ int dsb_destroy(dsb_sim *s)
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
     }
+    if (s->timer0) cudaEventDestroy(s->timer0);
+    if (s->timer1) cudaEventDestroy(s->timer1);
     cudaFree(s->d_grad);
     cudaFree(s->d_pos);
     cudaFree(s->d_phases);
@@ -519,6 +522,62 @@ int dsb_get_run_stats(dsb_sim *s, double *kernel_ms, int64_t *n_launches)
     if (rc) return rc;
     if (kernel_ms) *kernel_ms = s->kernel_ms;
     if (n_launches) *n_launches = s->n_launches;
+    return DSB_OK;
+}
+
+int dsb_timer_start(dsb_sim *s)
+{
+    if (!s) return fail(DSB_EINVAL, "null handle");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    if (!s->timer0) {
+        DSB_CUDA(cudaEventCreate(&s->timer0));
+        DSB_CUDA(cudaEventCreate(&s->timer1));
+    }
+    DSB_CUDA(cudaEventRecord(s->timer0, s->stream));
+    return DSB_OK;
+}
+
+int dsb_timer_stop(dsb_sim *s, double *elapsed_ms)
+{
+    if (!s || !elapsed_ms) return fail(DSB_EINVAL, "null argument");
+    if (!s->timer0) return fail(DSB_ESTATE, "dsb_timer_stop before dsb_timer_start");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    DSB_CUDA(cudaEventRecord(s->timer1, s->stream));
+    DSB_CUDA(cudaEventSynchronize(s->timer1));
+    float ms = 0.f;
+    DSB_CUDA(cudaEventElapsedTime(&ms, s->timer0, s->timer1));
+    *elapsed_ms = ms;
+    return DSB_OK;
+}
+
+int dsb_measure_fp64_peak(int32_t device, double *dfma_per_second)
+{
+    if (!dfma_per_second) return fail(DSB_EINVAL, "null argument");
+    DSB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DSB_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double *d_out = nullptr;
+    DSB_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    DSB_CUDA(cudaEventCreate(&e0));
+    DSB_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        DSB_CUDA(cudaEventRecord(e0));
+        dsb::fp64_peak_kernel<<<blocks, threads>>>(d_out, iters, 1.0 + 1e-9 * rep);
+        DSB_CUDA(cudaEventRecord(e1));
+        DSB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        DSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double rate = (double)blocks * threads * iters * dsb::kPeakChains / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    DSB_CUDA(cudaGetLastError());
+    *dfma_per_second = best;
     return DSB_OK;
 }
 

@@ -400,6 +400,28 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double *part
     if (threadIdx.x == 0) out[blockIdx.x] = s[0];
 }
 
+// ---------------------------------------------------------------- FP64 issue-rate probe
+
+constexpr int kPeakChains = 8;
+
+// kPeakChains independent DFMA chains per thread; nothing else in the loop.  Its rate is the
+// FP64 pipe's ceiling that bench.py's roofline is quoted against.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
+{
+    double a[kPeakChains];
+#pragma unroll
+    for (int k = 0; k < kPeakChains; ++k) a[k] = seed + k + threadIdx.x * 1e-6;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < kPeakChains; ++k) a[k] = __fma_rn(a[k], m, c);
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPeakChains; ++k) sum += a[k];
+    out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
 // ---------------------------------------------------------------- RNG state derivation
 
 // state[i] = J^(start + i) * splitmix64(seed), J = the 2^64-step jump of xoroshiro128+ as a

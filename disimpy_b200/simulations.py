@@ -246,6 +246,14 @@ class Walk:
                    "dsb_get_run_stats")
         return ms.value, n.value
 
+    def timer_start(self):
+        _lib.check(self._L.dsb_timer_start(self._h), "dsb_timer_start")
+
+    def timer_stop(self):
+        ms = ctypes.c_double(0)
+        _lib.check(self._L.dsb_timer_stop(self._h, ctypes.byref(ms)), "dsb_timer_stop")
+        return ms.value
+
     def close(self):
         if self._h:
             self._L.dsb_destroy(self._h)
