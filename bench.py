@@ -194,7 +194,7 @@ def main():
     # Global problem = world * N_WALKERS walkers; this rank's shard, resident in HBM.
     n_global = world * N_WALKERS
     lo, hi = simulations.shard_range(n_global, rank, world)
-    pos_all = simulations._fill_sphere(n_global, RADIUS, np.random.RandomState(SEED))
+    pos_all = simulations._fill_sphere(n_global, RADIUS, SEED)
     d_pos0 = torch.from_numpy(np.ascontiguousarray(pos_all[lo:hi])).cuda()
     params, keep = simulations.make_params(sub, hi - lo, lo, g, dt, step_l, SEED, 1000, 1e-13,
                                            device=local_rank)

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdisimpy_b200.so")
+# DISIMPY_B200_LIB lets kernel experiments (tools/kbench.py) load an alternative build
+LIB_PATH = os.environ.get("DISIMPY_B200_LIB") or os.path.join(_HERE, "libdisimpy_b200.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)
@@ -65,7 +66,7 @@ EXPORTS = [
     "dsb_measure_fp64_peak", "dsb_stream", "dsb_signal_dev", "dsb_destroy",
     "dsb_simulate", "dsb_rng_states", "dsb_fill_mesh", "dsb_mesh_subdivide",
     "dsb_mesh_subdivide_fetch", "dsb_triangle_box_overlap", "dsb_interval_sv_overlap",
-    "dsb_device_count", "dsb_last_error", "dsb_version",
+    "dsb_host_fill", "dsb_device_count", "dsb_last_error", "dsb_version",
 ]
 
 _lib = None
@@ -115,6 +116,8 @@ def lib():
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          c_int64_p, ctypes.POINTER(ctypes.c_void_p)]
         L.dsb_mesh_subdivide_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.dsb_host_fill.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64,
+                                    ctypes.c_void_p, ctypes.c_void_p]
         L.dsb_triangle_box_overlap.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.dsb_interval_sv_overlap.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
                                               ctypes.c_double, c_int64_p, c_int64_p]

@@ -222,6 +222,12 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
     d.inv_hx = m.n_sv[0] / (m.xs[m.n_sv[0]] - m.xs[0]);
     d.inv_hy = m.n_sv[1] / (m.ys[m.n_sv[1]] - m.ys[0]);
     d.inv_hz = m.n_sv[2] / (m.zs[m.n_sv[2]] - m.zs[0]);
+    const double *grid[3] = {m.xs, m.ys, m.zs};
+    for (int k = 0; k < 3; ++k) {
+        d.vox[k] = std::fabs(grid[k][m.n_sv[k]] - grid[k][0]);
+        d.inv_vox[k] = 1.0 / d.vox[k];
+        d.top[k] = grid[k][m.n_sv[k]];
+    }
     d.perm_prob = m.perm_prob;
     return DSB_OK;
 }

@@ -8,7 +8,16 @@
 
 namespace dsb {
 
-constexpr int kBlock = 128;          // threads (= walkers) per CTA
+#ifndef DSB_BLOCK
+#define DSB_BLOCK 128
+#endif
+#ifndef DSB_MIN_BLOCKS
+#define DSB_MIN_BLOCKS 1
+#endif
+#ifndef DSB_MESH_MIN_BLOCKS
+#define DSB_MESH_MIN_BLOCKS 4
+#endif
+constexpr int kBlock = DSB_BLOCK;    // threads (= walkers) per CTA
 constexpr int kMaxRegMeas = 4;       // measurements whose phase lives in registers
 constexpr int kTimeChunk = 8;        // steps buffered per phase pass when n_meas is larger
 
@@ -20,6 +29,9 @@ struct MeshDev {
     int len_xs, len_ys, len_zs;
     int nsv1, nsv2;
     double inv_hx, inv_hy, inv_hz;  // guesses only, never part of a result
+    double vox[3];      // |xs[-1] - xs[0]| per axis, the period of the lookup (simulations.py:660)
+    double inv_vox[3];  // 1 / vox, guess only
+    double top[3];      // xs[-1], ys[-1], zs[-1]: the image shift unit (simulations.py:943)
     double perm_prob;
 };
 
@@ -43,12 +55,15 @@ struct KParams {
 // ---------------------------------------------------------------- one time step, per substrate
 
 template <int SUB>
-__device__ __forceinline__ bool walker_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab);
+__device__ __forceinline__ bool walker_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
+                                            const bool live);
 
 // simulations.py:682-702
 template <>
-__device__ __forceinline__ bool walker_step<0>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab)
+__device__ __forceinline__ bool walker_step<0>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
+                                               const bool live)
 {
+    if (!live) return false;
     Vec3 s = random_step(rng, tab);
     pos.x = fma_(s.x, p.step_l, pos.x);
     pos.y = fma_(s.y, p.step_l, pos.y);
@@ -58,8 +73,10 @@ __device__ __forceinline__ bool walker_step<0>(Vec3 &pos, Rng &rng, const KParam
 
 // simulations.py:705-756
 template <>
-__device__ __forceinline__ bool walker_step<1>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab)
+__device__ __forceinline__ bool walker_step<1>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
+                                               const bool live)
 {
+    if (!live) return false;
     Vec3 s = random_step(rng, tab);
     double step_l = p.step_l;
     long long iter = 0;
@@ -88,8 +105,10 @@ __device__ __forceinline__ bool walker_step<1>(Vec3 &pos, Rng &rng, const KParam
 // simulations.py:759-816.  The position is rotated into the cylinder frame and back every
 // step, like the reference (the rounding of the round trip is part of the trajectory).
 template <>
-__device__ __forceinline__ bool walker_step<2>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab)
+__device__ __forceinline__ bool walker_step<2>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
+                                               const bool live)
 {
+    if (!live) return false;
     Vec3 s = random_step(rng, tab);
     Vec3 r0 = matvec3(p.R, pos);
     double step_l = p.step_l;
@@ -101,10 +120,17 @@ __device__ __forceinline__ bool walker_step<2>(Vec3 &pos, Rng &rng, const KParam
         if (d > 0 && d < step_l) {
             double X1 = fma_(d, s.y, r0.y), X2 = fma_(d, s.z, r0.z);
             double len = sqrt_(fma_(X2, X2, fma_(X1, X1, 0.0)));
+            // normal = (0, -X1, -X2) / len; 0 / len is +0 for every finite positive len
             Vec3 n;
-            n.x = div_(0.0, len);
-            n.y = div_(-X1, len);
-            n.z = div_(-X2, len);
+            double rc = rcp_refined(len);
+            bool ok = len > 0 && div_fast(-X1, len, rc, n.y);
+            ok = ok && div_fast(-X2, len, rc, n.z);
+            n.x = 0.0;
+            if (!ok) {
+                n.x = div_(0.0, len);
+                n.y = div_(-X1, len);
+                n.z = div_(-X2, len);
+            }
             reflect(r0, s, d, n, p.eps);
             step_l = sub_(step_l, add_(d, p.eps));
         } else {
@@ -121,8 +147,10 @@ __device__ __forceinline__ bool walker_step<2>(Vec3 &pos, Rng &rng, const KParam
 
 // simulations.py:819-875
 template <>
-__device__ __forceinline__ bool walker_step<3>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab)
+__device__ __forceinline__ bool walker_step<3>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
+                                               const bool live)
 {
+    if (!live) return false;
     Vec3 s = random_step(rng, tab);
     Vec3 r0 = matvec3(p.R, pos);
     double step_l = p.step_l;
@@ -161,66 +189,219 @@ __device__ __forceinline__ Tri load_tri(const double *tri9, int id)
     return t;
 }
 
-// floor(i / n) and i - floor(i/n)*n for a cell index outside [0, n): the reference does this
-// in FP64 (simulations.py:940-943); for |i| < 2^40 the integer result is identical.
-__device__ __forceinline__ void wrap_cell(long long i, int n, int &wrapped, double &shift_n)
+// ---- mesh: which grid cells does the remaining step segment overlap (simulations.py:929-934)
+
+// floor(x / V) with the rounding of the reference's div.rn + floor.  A reciprocal multiply is
+// within 4e-16 relative of the IEEE quotient, so whenever its fractional part is not within 1e-9
+// of an integer the two floors agree; otherwise the real division decides.
+__device__ __forceinline__ double floor_quotient(double x, double V, double invV)
 {
-    if (i < 0 || i > n - 1) {
-        long long q = i / n;
-        if (i % n != 0 && i < 0) --q;
-        wrapped = (int)(i - q * n);
-        shift_n = (double)q;
-    } else {
-        wrapped = (int)i;
-        shift_n = 0.0;
-    }
+    double qa = x * invV;
+    double fl = floor(qa);
+    double fr = qa - fl;
+    if (fr > 1e-9 && fr < 1.0 - 1e-9 && fabs(qa) < 1e5) return fl;
+    return floor(div_(x, V));
 }
 
-// simulations.py:878-1013
-template <>
-__device__ __forceinline__ bool walker_step<4>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab)
+// One end of the periodic cell range of an axis: the period index nq = floor(x / V) and the
+// cell index inside the base voxel (simulations.py:654-679).  upper == false: lower limit
+// (_ll_subvoxel_overlap), true: exclusive upper limit (_ul_subvoxel_overlap).
+__device__ __forceinline__ void axis_limit(const double *xs, int len, double V, double invV, double inv_h,
+                                           double x, bool upper, double &nq, int &base)
 {
-    const MeshDev &g = p.mesh;
-    Vec3 s = random_step(rng, tab);
-    double step_l = p.step_l;
-    long long iter = 0;
-    bool check = true;
-    int closest = 0;
-    while (check && step_l > 0 && iter < p.max_iter) {
-        ++iter;
-        double min_d = __longlong_as_double(0x7FF0000000000000LL);
+    nq = floor_quotient(x, V, invV);
+    double sh = fma_(-V, nq, x);
+    base = upper ? ul_overlap(xs, len, sh, inv_h) : ll_overlap(xs, len, sh, inv_h);
+}
+
+struct AxisCells {
+    double nq;       // period index of the first cell
+    int base;        // its index inside the base voxel (may equal n: first cell of the next image)
+    long long count; // number of cells, <= 0 when the range is empty
+};
+
+__device__ __forceinline__ AxisCells axis_cells(const double *xs, int len, double V, double invV, double inv_h,
+                                                double a, double b)
+{
+    AxisCells r;
+    double nq_hi;
+    int base_hi;
+    axis_limit(xs, len, V, invV, inv_h, fmin(a, b), false, r.nq, r.base);
+    axis_limit(xs, len, V, invV, inv_h, fmax(a, b), true, nq_hi, base_hi);
+    // global indices formed in FP64 like the reference (exact integers)
+    long long lo = __double2ll_rz(fma_(r.nq, (double)(len - 1), (double)r.base));
+    long long hi = __double2ll_rz(fma_(nq_hi, (double)(len - 1), (double)base_hi));
+    r.count = hi - lo;
+    return r;
+}
+
+// k-th cell of an axis range -> index inside the base voxel and periodic image number
+// (what simulations.py:940-945 derives with floor(x / (len - 1)))
+__device__ __forceinline__ void axis_cell(const AxisCells &r, int n, long long k, int &cell, double &image)
+{
+    long long j = (long long)r.base + k;
+    long long q = j / n;  // base >= 0, k >= 0
+    cell = (int)(j - q * n);
+    image = r.nq + (double)q;
+}
+
+constexpr int kCoopCells = 8;  // cells per walker and collision iteration tested cooperatively
+
+// Per-warp scratch: every lane publishes its ray and its short list of grid cells, then the 32
+// lanes share ALL listed (cell, triangle) tests of the warp evenly.
+struct MeshScratch {
+    double ray[6][32];            // position, unit step
+    int begin[kCoopCells][32];    // first entry of the cell in tri_idx
+    int cum[kCoopCells][32];      // inclusive running number of entries over the lane's cells
+    int image[3][kCoopCells][32]; // periodic image number of the cell per axis
+};
+
+// Closest triangle hit (d > 0) over every triangle listed in the cells the segment
+// [pos, pos + step_l * s] overlaps, visited in the reference's order (cells x -> y -> z, entries
+// ascending, strict "<" so the first minimum wins): simulations.py:936-983.
+__device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &sc, const int lane, const bool need,
+                                                 const Vec3 &pos, const Vec3 &s, const double step_l,
+                                                 double &min_d, int &closest)
+{
+    const unsigned full = 0xffffffffu;
+    const double inf = __longlong_as_double(0x7FF0000000000000LL);
+    min_d = inf;
+    int n_items = 0;
+    bool solo = false;
+    AxisCells ax, ay, az;
+    if (need) {
         // end point of the remaining segment: x uses a separately rounded product, y and z are
         // fused (that is how the reference's kernel was compiled)
         double ex = add_(pos.x, mul_(step_l, s.x));
         double ey = fma_(step_l, s.y, pos.y);
         double ez = fma_(step_l, s.z, pos.z);
-        long long lx = ll_overlap_periodic(g.xs, g.len_xs, pos.x, ex, g.inv_hx);
-        long long ly = ll_overlap_periodic(g.ys, g.len_ys, pos.y, ey, g.inv_hy);
-        long long lz = ll_overlap_periodic(g.zs, g.len_zs, pos.z, ez, g.inv_hz);
-        long long ux = ul_overlap_periodic(g.xs, g.len_xs, pos.x, ex, g.inv_hx);
-        long long uy = ul_overlap_periodic(g.ys, g.len_ys, pos.y, ey, g.inv_hy);
-        long long uz = ul_overlap_periodic(g.zs, g.len_zs, pos.z, ez, g.inv_hz);
-        for (long long xi = lx; xi < ux; ++xi) {
+        ax = axis_cells(g.xs, g.len_xs, g.vox[0], g.inv_vox[0], g.inv_hx, pos.x, ex);
+        ay = axis_cells(g.ys, g.len_ys, g.vox[1], g.inv_vox[1], g.inv_hy, pos.y, ey);
+        az = axis_cells(g.zs, g.len_zs, g.vox[2], g.inv_vox[2], g.inv_hz, pos.z, ez);
+        if (ax.count > 0 && ay.count > 0 && az.count > 0) {
+            const bool small = ax.count <= kCoopCells && ay.count <= kCoopCells && az.count <= kCoopCells &&
+                               ax.count * ay.count * az.count <= kCoopCells && fabs(ax.nq) < 1e9 &&
+                               fabs(ay.nq) < 1e9 && fabs(az.nq) < 1e9;
+            if (small) {
+                int c = 0;
+                for (int ix = 0; ix < (int)ax.count; ++ix) {
+                    int cx;
+                    double mx;
+                    axis_cell(ax, g.len_xs - 1, ix, cx, mx);
+                    for (int iy = 0; iy < (int)ay.count; ++iy) {
+                        int cy;
+                        double my;
+                        axis_cell(ay, g.len_ys - 1, iy, cy, my);
+                        for (int iz = 0; iz < (int)az.count; ++iz) {
+                            int cz;
+                            double mz;
+                            axis_cell(az, g.len_zs - 1, iz, cz, mz);
+                            int2 r = __ldg(g.cell_rng + ((long long)cx * g.nsv1 + cy) * g.nsv2 + cz);
+                            n_items += r.y - r.x;
+                            sc.begin[c][lane] = r.x;
+                            sc.cum[c][lane] = n_items;
+                            sc.image[0][c][lane] = (int)mx;
+                            sc.image[1][c][lane] = (int)my;
+                            sc.image[2][c][lane] = (int)mz;
+                            ++c;
+                        }
+                    }
+                }
+                sc.ray[0][lane] = pos.x; sc.ray[1][lane] = pos.y; sc.ray[2][lane] = pos.z;
+                sc.ray[3][lane] = s.x; sc.ray[4][lane] = s.y; sc.ray[5][lane] = s.z;
+            } else {
+                solo = true;
+            }
+        }
+    }
+    __syncwarp();
+
+    // exclusive prefix sum of the lanes' item counts
+    int incl = n_items;
+#pragma unroll
+    for (int st = 1; st < 32; st <<= 1) {
+        int v = __shfl_up_sync(full, incl, st);
+        if (lane >= st) incl += v;
+    }
+    const int excl = incl - n_items;
+    const int total = __shfl_sync(full, incl, 31);
+
+    for (int base = 0; base < total; base += 32) {
+        const int j = base + lane;
+        // owner = last lane whose first item index is <= j
+        int owner = 0;
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) {
+            int cand = owner + st;
+            int first = __shfl_sync(full, excl, cand & 31);
+            if (cand < 32 && first <= j) owner = cand;
+        }
+        const int owner_first = __shfl_sync(full, excl, owner);
+        double d = inf;
+        int id = -1;
+        if (j < total) {
+            const int i = j - owner_first;
+            int c = 0;
+            while (i >= sc.cum[c][owner]) ++c;
+            const int entry = sc.begin[c][owner] + i - (c ? sc.cum[c - 1][owner] : 0);
+            id = __ldg(g.tri_idx + entry);
+            const Tri tr = load_tri(g.tri9, id);
+            const int mx = sc.image[0][c][owner], my = sc.image[1][c][owner], mz = sc.image[2][c][owner];
+            Vec3 o, dir;
+            // walker moved into the base voxel: r0 - shift_n * xs[-1] (simulations.py:943, 970-971)
+            o.x = sub_(sc.ray[0][owner], mx == 0 ? 0.0 : mul_((double)mx, g.top[0]));
+            o.y = sub_(sc.ray[1][owner], my == 0 ? 0.0 : mul_((double)my, g.top[1]));
+            o.z = sub_(sc.ray[2][owner], mz == 0 ? 0.0 : mul_((double)mz, g.top[2]));
+            dir.x = sc.ray[3][owner]; dir.y = sc.ray[4][owner]; dir.z = sc.ray[5][owner];
+            const double t = ray_triangle(tr, o, dir);
+            if (t > 0) d = t;
+        }
+        // segmented running minimum over lanes that serve the same owner; on ties the earlier
+        // item (lower lane) wins, like the reference's strict "<" in visiting order
+#pragma unroll
+        for (int st = 1; st < 32; st <<= 1) {
+            double dp = __shfl_up_sync(full, d, st);
+            int ip = __shfl_up_sync(full, id, st);
+            int op = __shfl_up_sync(full, owner, st);
+            if (lane >= st && op == owner && dp <= d) {
+                d = dp;
+                id = ip;
+            }
+        }
+        // every owner with items in this round takes the result of its segment's last lane
+        const int lo = max(excl, base), hi = min(excl + n_items, base + 32);
+        const bool mine = lo < hi;
+        const int src = mine ? hi - 1 - base : lane;
+        const double ds = __shfl_sync(full, d, src);
+        const int is = __shfl_sync(full, id, src);
+        if (mine && ds < min_d) {
+            min_d = ds;
+            closest = is;
+        }
+    }
+    __syncwarp();
+
+    if (solo) {  // more cells than the shared table holds: this lane walks its own cells
+        for (long long ix = 0; ix < ax.count; ++ix) {
             int cx;
-            double snx;
-            wrap_cell(xi, g.len_xs - 1, cx, snx);
-            double tx = sub_(pos.x, snx == 0.0 ? 0.0 : mul_(snx, g.xs[g.len_xs - 1]));
-            for (long long yi = ly; yi < uy; ++yi) {
+            double mx;
+            axis_cell(ax, g.len_xs - 1, ix, cx, mx);
+            const double tx = sub_(pos.x, mx == 0.0 ? 0.0 : mul_(mx, g.top[0]));
+            for (long long iy = 0; iy < ay.count; ++iy) {
                 int cy;
-                double sny;
-                wrap_cell(yi, g.len_ys - 1, cy, sny);
-                double ty = sub_(pos.y, sny == 0.0 ? 0.0 : mul_(sny, g.ys[g.len_ys - 1]));
-                for (long long zi = lz; zi < uz; ++zi) {
+                double my;
+                axis_cell(ay, g.len_ys - 1, iy, cy, my);
+                const double ty = sub_(pos.y, my == 0.0 ? 0.0 : mul_(my, g.top[1]));
+                for (long long iz = 0; iz < az.count; ++iz) {
                     int cz;
-                    double snz;
-                    wrap_cell(zi, g.len_zs - 1, cz, snz);
-                    double tz = sub_(pos.z, snz == 0.0 ? 0.0 : mul_(snz, g.zs[g.len_zs - 1]));
-                    Vec3 tr0 = {tx, ty, tz};
-                    int2 rng_c = __ldg(g.cell_rng + ((long long)cx * g.nsv1 + cy) * g.nsv2 + cz);
-                    for (int i = rng_c.x; i < rng_c.y; ++i) {
-                        int id = __ldg(g.tri_idx + i);
-                        Tri tr = load_tri(g.tri9, id);
-                        double d = ray_triangle(tr, tr0, s);
+                    double mz;
+                    axis_cell(az, g.len_zs - 1, iz, cz, mz);
+                    const double tz = sub_(pos.z, mz == 0.0 ? 0.0 : mul_(mz, g.top[2]));
+                    const Vec3 tr0 = {tx, ty, tz};
+                    const int2 r = __ldg(g.cell_rng + ((long long)cx * g.nsv1 + cy) * g.nsv2 + cz);
+                    for (int i = r.x; i < r.y; ++i) {
+                        const int id = __ldg(g.tri_idx + i);
+                        const double d = ray_triangle(load_tri(g.tri9, id), tr0, s);
                         if (d > 0 && d < min_d) {
                             closest = id;
                             min_d = d;
@@ -229,17 +410,42 @@ __device__ __forceinline__ bool walker_step<4>(Vec3 &pos, Rng &rng, const KParam
                 }
             }
         }
-        if (min_d > step_l) {
-            check = false;
-        } else {
-            double u = u01_f64(rng_next(rng));
-            Tri tr = load_tri(g.tri9, closest);
-            Vec3 n = triangle_normal(tr);
-            if (g.perm_prob < u)
-                reflect(pos, s, min_d, n, p.eps);
-            else
-                cross_membrane(pos, s, min_d, n, p.eps);
-            step_l = sub_(step_l, min_d);
+    }
+}
+
+// simulations.py:878-1013.  Warp-synchronous: every lane of the warp must call it (live == false
+// for lanes without a walker); the collision search of each iteration is shared by the warp.
+template <>
+__device__ __forceinline__ bool walker_step<4>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
+                                               const bool live)
+{
+    __shared__ MeshScratch s_scratch[kBlock / 32];
+    MeshScratch &sc = s_scratch[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const MeshDev &g = p.mesh;
+    Vec3 s = random_step(rng, tab);
+    double step_l = p.step_l;
+    long long iter = 0;
+    bool check = live;
+    int closest = 0;
+    for (;;) {
+        const bool need = check && step_l > 0 && iter < p.max_iter;
+        if (!__any_sync(0xffffffffu, need)) break;
+        if (need) ++iter;
+        double min_d;
+        mesh_closest_hit(g, sc, lane, need, pos, s, step_l, min_d, closest);
+        if (need) {
+            if (min_d > step_l) {
+                check = false;
+            } else {
+                double u = u01_f64(rng_next(rng));
+                Vec3 n = triangle_normal(load_tri(g.tri9, closest));
+                if (g.perm_prob < u)
+                    reflect(pos, s, min_d, n, p.eps);
+                else
+                    cross_membrane(pos, s, min_d, n, p.eps);
+                step_l = sub_(step_l, min_d);
+            }
         }
     }
     pos.x = fma_(step_l, s.x, pos.x);
@@ -292,7 +498,7 @@ __device__ __forceinline__ void block_signal(const KParams &p, bool valid, Phase
 // are buffered in registers, then each measurement's phase makes one round trip through its
 // (coalesced, L2-resident) row of `phases` per chunk instead of one per step.
 template <int SUB, int MR>
-__global__ void __launch_bounds__(kBlock) walk_kernel(const __grid_constant__ KParams p)
+__global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : DSB_MIN_BLOCKS) walk_kernel(const __grid_constant__ KParams p)
 {
     __shared__ double s_tab[16];
     if (threadIdx.x < 16) s_tab[threadIdx.x] = __longlong_as_double((long long)c_sincos_tab[threadIdx.x]);
@@ -317,16 +523,17 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const __grid_constant__ KP
         double ph[MR];
 #pragma unroll
         for (int m = 0; m < MR; ++m) ph[m] = (active && p.t0 > 0) ? p.phases[(long long)m * N + w] : 0.0;
-        if (active) {
-            for (int t = p.t0; t < p.t1; ++t) {
-                exc |= walker_step<SUB>(pos, rng, p, s_tab);
+        // the time loop is uniform over the block (the mesh step shares work inside each warp)
+        for (int t = p.t0; t < p.t1; ++t) {
+            exc |= walker_step<SUB>(pos, rng, p, s_tab, active);
 #pragma unroll
-                for (int m = 0; m < MR; ++m) {
-                    const double *g = p.grad + ((long long)m * p.n_t + t) * 3;
-                    double gx = __ldg(g), gy = __ldg(g + 1), gz = __ldg(g + 2);
-                    ph[m] = fma_(p.gamma_dt, fma_(gz, pos.z, fma_(gx, pos.x, mul_(gy, pos.y))), ph[m]);
-                }
+            for (int m = 0; m < MR; ++m) {
+                const double *g = p.grad + ((long long)m * p.n_t + t) * 3;
+                double gx = __ldg(g), gy = __ldg(g + 1), gz = __ldg(g + 2);
+                ph[m] = fma_(p.gamma_dt, fma_(gz, pos.z, fma_(gx, pos.x, mul_(gy, pos.y))), ph[m]);
             }
+        }
+        if (active) {
 #pragma unroll
             for (int m = 0; m < MR; ++m) p.phases[(long long)m * N + w] = ph[m];
         }
@@ -343,18 +550,18 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const __grid_constant__ KP
                 return v;
             });
     } else {
-        if (active) {
-            if (p.t0 == 0)
-                for (int m = 0; m < p.n_meas; ++m) p.phases[(long long)m * N + w] = 0.0;
-            Vec3 buf[kTimeChunk];
-            for (int t = p.t0; t < p.t1; t += kTimeChunk) {
-                const int cnt = min(kTimeChunk, p.t1 - t);
+        if (active && p.t0 == 0)
+            for (int m = 0; m < p.n_meas; ++m) p.phases[(long long)m * N + w] = 0.0;
+        Vec3 buf[kTimeChunk];
+        for (int t = p.t0; t < p.t1; t += kTimeChunk) {
+            const int cnt = min(kTimeChunk, p.t1 - t);
 #pragma unroll
-                for (int k = 0; k < kTimeChunk; ++k)
-                    if (k < cnt) {
-                        exc |= walker_step<SUB>(pos, rng, p, s_tab);
-                        buf[k] = pos;
-                    }
+            for (int k = 0; k < kTimeChunk; ++k)
+                if (k < cnt) {
+                    exc |= walker_step<SUB>(pos, rng, p, s_tab, active);
+                    buf[k] = pos;
+                }
+            if (active)
                 for (int m = 0; m < p.n_meas; ++m) {
                     double *row = p.phases + (long long)m * N + w;
                     double a = *row;
@@ -367,7 +574,8 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const __grid_constant__ KP
                         }
                     *row = a;
                 }
-            }
+        }
+        if (active) {
             if (exc) p.iter_exc[w] = 1;
             else exc = p.iter_exc[w] != 0;
         }

@@ -27,50 +27,43 @@ from .gradients import GAMMA  # noqa: F401  (same module-level name as the refer
 # ----------------------------------------------------------------------------------------
 # host-side initial positions (simulations.py:346-418): sequential rejection sampling from
 # the MT19937 stream seeded with ``seed`` -- Numba's CPU generator after _set_seed(seed) is
-# np.random.RandomState(seed) -- vectorised in blocks, same acceptance order.
+# np.random.RandomState(seed) -- done natively in csrc/dsb_hostfill.cpp, same acceptance order.
 
-def _rejection_sample(rs, n, scale, dim, accept):
-    out = np.zeros((0, dim))
-    while len(out) < n:
-        k = max(4096, int((n - len(out)) * 2.3))
-        cand = (rs.random_sample((k, dim)) - 0.5) * 2 * scale
-        out = np.concatenate([out, cand[accept(cand)]])
-    return out[:n]
-
-
-def _fill_circle(n, radius, rs=None):
-    """n points uniform in a disc (simulations.py:353-366)."""
-    rs = np.random.RandomState() if rs is None else rs
-    return _rejection_sample(rs, n, radius, 2, lambda p: np.sqrt((p * p).sum(axis=1)) < radius)
+def _host_fill(shape, n, seed, scale, dim):
+    out = np.zeros((n, dim))
+    sc = _lib.f64(np.atleast_1d(scale))
+    rc = _lib.lib().dsb_host_fill(shape, n, seed, _lib.ptr(sc), _lib.ptr(out))
+    if rc != 0:
+        raise ValueError("Seed must be between 0 and 2**32 - 1")
+    return out
 
 
-def _fill_sphere(n, radius, rs=None):
+def _fill_circle(n, radius, seed):
+    """n points uniform in a disc (simulations.py:353-366) from the MT19937 stream of ``seed``."""
+    return _host_fill(0, n, seed, radius, 2)
+
+
+def _fill_sphere(n, radius, seed):
     """n points uniform in a ball (simulations.py:369-382)."""
-    rs = np.random.RandomState() if rs is None else rs
-    return _rejection_sample(rs, n, radius, 3, lambda p: np.sqrt((p * p).sum(axis=1)) < radius)
+    return _host_fill(1, n, seed, radius, 3)
 
 
-def _fill_ellipsoid(n, semiaxes, rs=None):
+def _fill_ellipsoid(n, semiaxes, seed):
     """n points uniform in an axis-aligned ellipsoid (simulations.py:385-399)."""
-    rs = np.random.RandomState() if rs is None else rs
-
-    def inside(p):
-        q = (p / semiaxes) ** 2
-        return q[:, 0] + q[:, 1] + q[:, 2] < 1
-    return _rejection_sample(rs, n, semiaxes, 3, inside)
+    return _host_fill(2, n, seed, semiaxes, 3)
 
 
-def _initial_positions_cylinder(n_walkers, radius, R, rs=None):
+def _initial_positions_cylinder(n_walkers, radius, R, seed):
     """Points in the cross-section of a cylinder, rotated to the lab frame by R
     (simulations.py:402-409)."""
     positions = np.zeros((n_walkers, 3))
-    positions[:, 1:3] = _fill_circle(n_walkers, radius, rs)
+    positions[:, 1:3] = _fill_circle(n_walkers, radius, seed)
     return np.matmul(R, positions.T).T
 
 
-def _initial_positions_ellipsoid(n_walkers, semiaxes, R, rs=None):
+def _initial_positions_ellipsoid(n_walkers, semiaxes, R, seed):
     """Points in an ellipsoid, rotated to the lab frame by R (simulations.py:412-418)."""
-    return np.matmul(R, _fill_ellipsoid(n_walkers, semiaxes, rs).T).T
+    return np.matmul(R, _fill_ellipsoid(n_walkers, semiaxes, seed).T).T
 
 
 def _fill_mesh(n_points, substrate, intra, seed, cuda_bs=128):
@@ -336,7 +329,6 @@ def simulation(
     # Same seeding side effect as the reference (simulations.py:1169-1170): NumPy's global
     # generator is reseeded; the host samplers use an MT19937 stream with the same seed.
     np.random.seed(seed)
-    rs = np.random.RandomState(seed)
     step_l = np.sqrt(6 * diffusivity * dt)
 
     if not quiet:
@@ -349,11 +341,11 @@ def simulation(
         positions = np.zeros((n_walkers, 3))
     elif substrate.type == "cylinder":
         R = utils.vec2vec_rotmat(substrate.orientation, np.array([1.0, 0, 0]))
-        positions = _initial_positions_cylinder(n_walkers, substrate.radius, np.linalg.inv(R), rs)
+        positions = _initial_positions_cylinder(n_walkers, substrate.radius, np.linalg.inv(R), seed)
     elif substrate.type == "sphere":
-        positions = _fill_sphere(n_walkers, substrate.radius, rs)
+        positions = _fill_sphere(n_walkers, substrate.radius, seed)
     elif substrate.type == "ellipsoid":
-        positions = _initial_positions_ellipsoid(n_walkers, substrate.semiaxes, substrate.R, rs)
+        positions = _initial_positions_ellipsoid(n_walkers, substrate.semiaxes, substrate.R, seed)
     else:
         if isinstance(substrate.init_pos, np.ndarray):
             if n_walkers != substrate.init_pos.shape[0]:

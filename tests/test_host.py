@@ -229,8 +229,7 @@ def test_initial_positions_match_reference_stream():
     from disimpy_b200 import simulations
     from oracle import oracle as O
     import types
-    rs = np.random.RandomState(123)
-    pts = simulations._fill_sphere(5000, 3e-6, rs)
+    pts = simulations._fill_sphere(5000, 3e-6, 123)
     assert np.all(np.linalg.norm(pts, axis=1) < 3e-6)
     seq = np.random.RandomState(123)
     manual = []
@@ -242,10 +241,17 @@ def test_initial_positions_match_reference_stream():
     sub = types.SimpleNamespace(type="sphere", radius=3e-6)
     assert np.array_equal(pts, O.initial_positions(sub, 5000, 123))
     ax = np.array([3e-6, 2e-6, 1e-6])
-    e = simulations._fill_ellipsoid(2000, ax, np.random.RandomState(5))
+    e = simulations._fill_ellipsoid(2000, ax, 5)
     assert np.all(((e / ax) ** 2).sum(axis=1) < 1)
-    c = simulations._fill_circle(2000, 1e-6, np.random.RandomState(5))
+    c = simulations._fill_circle(2000, 1e-6, 5)
     assert c.shape == (2000, 2) and np.all(np.linalg.norm(c, axis=1) < 1e-6)
+    # ellipsoid / disc streams against the oracle's NumPy restatement
+    esub = types.SimpleNamespace(type="ellipsoid", semiaxes=ax, R=np.eye(3))
+    assert np.array_equal(e, O.initial_positions(esub, 2000, 5))
+    csub = types.SimpleNamespace(type="cylinder", radius=1e-6, orientation=np.array([1.0, 0, 0]))
+    assert np.array_equal(c, O.initial_positions(csub, 2000, 5)[:, 1:3])
+    with pytest.raises(ValueError):
+        simulations._fill_sphere(10, 1e-6, 2 ** 32)
 
 
 def test_simulation_argument_validation():
