@@ -4,6 +4,7 @@
 #include "dsb_fill.cuh"
 #include "dsb_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -138,15 +139,17 @@ int launch_rng_init(int device, uint64_t seed, uint64_t start, int64_t n, ulongl
 // ------------------------------------------------------------- mesh upload
 
 struct MeshBuffers {
-    double *tri9 = nullptr;
+    double *tri = nullptr;
     int *tri_idx = nullptr;
+    uint4 *entry = nullptr;
     int2 *cell_rng = nullptr;
     double *xs = nullptr, *ys = nullptr, *zs = nullptr;
     dsb::MeshDev dev{};
     void release()
     {
-        cudaFree(tri9);
+        cudaFree(tri);
         cudaFree(tri_idx);
+        cudaFree(entry);
         cudaFree(cell_rng);
         cudaFree(xs);
         cudaFree(ys);
@@ -156,8 +159,8 @@ struct MeshBuffers {
 };
 
 // Re-lays the reference's mesh arrays out for the kernels: int64 indices become int32, and the
-// three vertex gathers per test (simulations.py:100-118) become one 72-byte record per triangle
-// holding A, B-A, C-A.
+// three vertex gathers per test (simulations.py:100-118) become one 16-byte aligned 80-byte
+// record per triangle holding A, B-A, C-A (72 bytes) and a pad, read with five 128-bit loads.
 int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
 {
     if (!m.vertices || !m.faces || !m.xs || !m.ys || !m.zs || !m.subvoxel_indices ||
@@ -169,24 +172,47 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
         if (m.n_sv[k] <= 0 || m.n_sv[k] > 1 << 20) return fail(DSB_EINVAL, "mesh: n_sv out of range");
     const int64_t n_cells = m.n_sv[0] * m.n_sv[1] * m.n_sv[2];
     if (n_cells > 0x7fffffffLL) return fail(DSB_EINVAL, "mesh: too many subvoxels");
-    std::vector<double> tri9((size_t)m.n_faces * 9);
+    std::vector<double> tri((size_t)m.n_faces * dsb::kTriStride, 0.0);
     for (int64_t f = 0; f < m.n_faces; ++f) {
         const int64_t *idx = m.faces + 3 * f;
         for (int c = 0; c < 3; ++c)
             if (idx[c] < 0 || idx[c] >= m.n_vertices) return fail(DSB_EINVAL, "mesh: face index out of range");
         const double *A = m.vertices + 3 * idx[0], *B = m.vertices + 3 * idx[1], *C = m.vertices + 3 * idx[2];
-        double *o = &tri9[(size_t)f * 9];
+        double *o = &tri[(size_t)f * dsb::kTriStride];
         for (int c = 0; c < 3; ++c) {
             o[c] = A[c];
             o[3 + c] = B[c] - A[c];
             o[6 + c] = C[c] - A[c];
         }
     }
+    // Box of every triangle on a 15-bit grid over [0, xs[-1]] x [0, ys[-1]] x [0, zs[-1]], rounded
+    // outwards by a grid unit, for the kernels' pre-test; stored as (lo, 32767 - hi) halfwords so
+    // that "boxes meet" is one direction of comparison for all six numbers.
+    const double tops[3] = {m.xs[m.n_sv[0]], m.ys[m.n_sv[1]], m.zs[m.n_sv[2]]};
+    std::vector<uint4> box((size_t)m.n_faces);
+    for (int64_t f = 0; f < m.n_faces; ++f) {
+        const int64_t *idx = m.faces + 3 * f;
+        unsigned lo[3], hi[3];
+        for (int k = 0; k < 3; ++k) {
+            const double a = m.vertices[3 * idx[0] + k], b = m.vertices[3 * idx[1] + k], c = m.vertices[3 * idx[2] + k];
+            const double mn = std::min(a, std::min(b, c)), mx = std::max(a, std::max(b, c));
+            const double scale = 32767.0 / tops[k];
+            double ql = std::floor(mn * scale) - 1.0, qh = std::ceil(mx * scale) + 1.0;
+            if (!(ql > 0.0)) ql = 0.0;        // also NaN: never filtered out
+            if (!(qh < 32767.0)) qh = 32767.0;
+            if (!(mn == mn) || !(mx == mx)) ql = 0.0, qh = 32767.0;
+            lo[k] = (unsigned)std::min(ql, 32767.0);
+            hi[k] = 32767u - (unsigned)std::max(qh, 0.0);
+        }
+        box[(size_t)f] = make_uint4((unsigned)f, lo[0] | (lo[1] << 16), lo[2] | (hi[0] << 16), hi[1] | (hi[2] << 16));
+    }
     std::vector<int> tri_idx((size_t)m.n_triangle_indices);
+    std::vector<uint4> entry((size_t)m.n_triangle_indices + 1);
     for (int64_t i = 0; i < m.n_triangle_indices; ++i) {
         if (m.triangle_indices[i] < 0 || m.triangle_indices[i] >= m.n_faces)
             return fail(DSB_EINVAL, "mesh: triangle index out of range");
         tri_idx[(size_t)i] = (int)m.triangle_indices[i];
+        entry[(size_t)i] = box[(size_t)m.triangle_indices[i]];
     }
     std::vector<int2> cells((size_t)n_cells);
     for (int64_t c = 0; c < n_cells; ++c) {
@@ -194,13 +220,15 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
         if (a < 0 || b < a || b > m.n_triangle_indices) return fail(DSB_EINVAL, "mesh: subvoxel range out of bounds");
         cells[(size_t)c] = make_int2((int)a, (int)b);
     }
-    DSB_CUDA(cudaMalloc(&mb.tri9, tri9.size() * sizeof(double)));
+    DSB_CUDA(cudaMalloc(&mb.tri, tri.size() * sizeof(double)));
     DSB_CUDA(cudaMalloc(&mb.tri_idx, (tri_idx.size() + 1) * sizeof(int)));
+    DSB_CUDA(cudaMalloc(&mb.entry, entry.size() * sizeof(uint4)));
+    DSB_CUDA(cudaMemcpy(mb.entry, entry.data(), entry.size() * sizeof(uint4), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaMalloc(&mb.cell_rng, cells.size() * sizeof(int2)));
     DSB_CUDA(cudaMalloc(&mb.xs, (m.n_sv[0] + 1) * sizeof(double)));
     DSB_CUDA(cudaMalloc(&mb.ys, (m.n_sv[1] + 1) * sizeof(double)));
     DSB_CUDA(cudaMalloc(&mb.zs, (m.n_sv[2] + 1) * sizeof(double)));
-    DSB_CUDA(cudaMemcpy(mb.tri9, tri9.data(), tri9.size() * sizeof(double), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaMemcpy(mb.tri, tri.data(), tri.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (!tri_idx.empty())
         DSB_CUDA(cudaMemcpy(mb.tri_idx, tri_idx.data(), tri_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaMemcpy(mb.cell_rng, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -208,8 +236,9 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
     DSB_CUDA(cudaMemcpy(mb.ys, m.ys, (m.n_sv[1] + 1) * sizeof(double), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaMemcpy(mb.zs, m.zs, (m.n_sv[2] + 1) * sizeof(double), cudaMemcpyHostToDevice));
     dsb::MeshDev &d = mb.dev;
-    d.tri9 = mb.tri9;
+    d.tri = mb.tri;
     d.tri_idx = mb.tri_idx;
+    d.entry = mb.entry;
     d.cell_rng = mb.cell_rng;
     d.xs = mb.xs;
     d.ys = mb.ys;
@@ -227,6 +256,7 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
         d.vox[k] = std::fabs(grid[k][m.n_sv[k]] - grid[k][0]);
         d.inv_vox[k] = 1.0 / d.vox[k];
         d.top[k] = grid[k][m.n_sv[k]];
+        d.qscale[k] = 32767.0 / d.top[k];
     }
     d.perm_prob = m.perm_prob;
     return DSB_OK;
@@ -443,7 +473,7 @@ int dsb_run(dsb_sim *s, int64_t t0, int64_t t1)
     kp.t0 = (int)t0;
     kp.t1 = (int)t1;
     kp.finalize = t1 == P.n_t;
-    kp.max_iter = P.max_iter;
+    kp.max_iter = (int)std::min<int64_t>(P.max_iter, 0x7fffffff);
     kp.step_l = P.step_l;
     kp.gamma_dt = P.dt * 267.513e6;  // dt * GAMMA (gradients.py:13), one rounding like the reference
     kp.eps = P.epsilon;

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(128) fill_mesh_kernel(const MeshDev g, double 
                         break;
                     }
                     int tri = __ldg(g.tri_idx + i);
-                    double d = ray_triangle(load_tri(g.tri9, tri), pt, ray);
+                    double d = ray_triangle(load_tri(g.tri, tri), pt, ray);
                     if (d > 0) {
                         bool seen = false;
                         for (int j = 0; j < n_hits; ++j)

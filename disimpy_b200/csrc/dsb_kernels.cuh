@@ -22,8 +22,9 @@ constexpr int kMaxRegMeas = 4;       // measurements whose phase lives in regist
 constexpr int kTimeChunk = 8;        // steps buffered per phase pass when n_meas is larger
 
 struct MeshDev {
-    const double *tri9;     // (n_faces, 9): A, B-A, C-A
+    const double *tri;      // (n_faces, kTriStride): A, B-A, C-A, pad
     const int *tri_idx;     // (K,) triangle ids, cell after cell (reference order)
+    const uint4 *entry;     // (K,) per list entry: triangle id, box (lo, 32767 - hi) on a 15-bit grid, 3 x 2 halfwords
     const int2 *cell_rng;   // (n_cells,) [begin, end) into tri_idx
     const double *xs, *ys, *zs;
     int len_xs, len_ys, len_zs;
@@ -32,6 +33,7 @@ struct MeshDev {
     double vox[3];      // |xs[-1] - xs[0]| per axis, the period of the lookup (simulations.py:660)
     double inv_vox[3];  // 1 / vox, guess only
     double top[3];      // xs[-1], ys[-1], zs[-1]: the image shift unit (simulations.py:943)
+    double qscale[3];   // 32767 / top: the 15-bit grid of the box filter
     double perm_prob;
 };
 
@@ -40,7 +42,7 @@ struct KParams {
     int n_meas, n_t;
     int t0, t1;
     int finalize;  // t1 == n_t: also emit per-block sum(cos phase) partials
-    long long max_iter;
+    int max_iter;  // clamped to INT_MAX by the host
     double step_l, gamma_dt, eps, radius;
     double R[9], Rinv[9], ax[3];
     const double *grad;         // (n_meas, n_t, 3)
@@ -54,14 +56,8 @@ struct KParams {
 
 // ---------------------------------------------------------------- one time step, per substrate
 
-template <int SUB>
-__device__ __forceinline__ bool walker_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
-                                            const bool live);
-
 // simulations.py:682-702
-template <>
-__device__ __forceinline__ bool walker_step<0>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
-                                               const bool live)
+__device__ __forceinline__ bool free_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab, const bool live)
 {
     if (!live) return false;
     Vec3 s = random_step(rng, tab);
@@ -71,121 +67,116 @@ __device__ __forceinline__ bool walker_step<0>(Vec3 &pos, Rng &rng, const KParam
     return false;
 }
 
-// simulations.py:705-756
-template <>
-__device__ __forceinline__ bool walker_step<1>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
-                                               const bool live)
+// ---- analytic substrates (sphere, cylinder, ellipsoid): a time step taken apart into the pieces
+// the collision loop of the reference is made of, so that the time loop can either run them
+// back to back (walker_step) or park colliding walkers and bounce them in batches (walk_kernel).
+
+struct Flight {      // one time step in progress
+    Vec3 s, r0;      // unit step and position, in the substrate's frame
+    double step_l;   // length still to travel
+    double d;        // distance to the wall found by the last probe
+    int iter;        // intersection checks made in this step
+};
+
+// new random direction; position into the substrate frame (simulations.py:722-728, 778-787,
+// 838-847).  The step is not rotated in, like the reference.
+template <int SUB>
+__device__ __forceinline__ void begin_step(const Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
+                                           Flight &f)
 {
-    if (!live) return false;
-    Vec3 s = random_step(rng, tab);
-    double step_l = p.step_l;
-    long long iter = 0;
-    bool check = true;
-    while (check && step_l > 0 && iter < p.max_iter) {
-        ++iter;
-        double d = line_sphere(pos, s, p.radius);
-        if (d > 0 && d < step_l) {
-            Vec3 n;
-            n.x = -fma_(d, s.x, pos.x);
-            n.y = -fma_(d, s.y, pos.y);
-            n.z = -fma_(d, s.z, pos.z);
-            n = normalize3(n);
-            reflect(pos, s, d, n, p.eps);
-            step_l = sub_(step_l, add_(d, p.eps));
-        } else {
-            check = false;
-        }
-    }
-    pos.x = fma_(step_l, s.x, pos.x);
-    pos.y = fma_(step_l, s.y, pos.y);
-    pos.z = fma_(step_l, s.z, pos.z);
-    return iter >= p.max_iter;
+    f.s = random_step(rng, tab);
+    if constexpr (SUB == 2 || SUB == 3) f.r0 = matvec3(p.R, pos);
+    else f.r0 = pos;
+    f.step_l = p.step_l;
+    f.iter = 0;
 }
 
-// simulations.py:759-816.  The position is rotated into the cylinder frame and back every
-// step, like the reference (the rounding of the round trip is part of the trajectory).
-template <>
-__device__ __forceinline__ bool walker_step<2>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
-                                               const bool live)
+// Loop guard + intersection check of the reference's while loop (simulations.py:730-733,
+// 789-792, 849-852): true when the walker hits the wall within the remaining length (f.d = the
+// distance), false when the step can be completed.
+template <int SUB>
+__device__ __forceinline__ bool probe(Flight &f, const KParams &p)
 {
-    if (!live) return false;
-    Vec3 s = random_step(rng, tab);
-    Vec3 r0 = matvec3(p.R, pos);
-    double step_l = p.step_l;
-    long long iter = 0;
-    bool check = true;
-    while (check && step_l > 0 && iter < p.max_iter) {
-        ++iter;
-        double d = line_circle(r0, s, p.radius);
-        if (d > 0 && d < step_l) {
-            double X1 = fma_(d, s.y, r0.y), X2 = fma_(d, s.z, r0.z);
-            double len = sqrt_(fma_(X2, X2, fma_(X1, X1, 0.0)));
-            // normal = (0, -X1, -X2) / len; 0 / len is +0 for every finite positive len
-            Vec3 n;
-            double rc = rcp_refined(len);
-            bool ok = len > 0 && div_fast(-X1, len, rc, n.y);
-            ok = ok && div_fast(-X2, len, rc, n.z);
-            n.x = 0.0;
-            if (!ok) {
-                n.x = div_(0.0, len);
-                n.y = div_(-X1, len);
-                n.z = div_(-X2, len);
-            }
-            reflect(r0, s, d, n, p.eps);
-            step_l = sub_(step_l, add_(d, p.eps));
-        } else {
-            check = false;
-        }
-    }
-    s = matvec3(p.Rinv, s);
-    r0 = matvec3(p.Rinv, r0);
-    pos.x = fma_(step_l, s.x, r0.x);
-    pos.y = fma_(step_l, s.y, r0.y);
-    pos.z = fma_(step_l, s.z, r0.z);
-    return iter >= p.max_iter;
+    if (!(f.step_l > 0) || f.iter >= p.max_iter) return false;
+    ++f.iter;
+    if constexpr (SUB == 1) f.d = line_sphere(f.r0, f.s, p.radius);
+    else if constexpr (SUB == 2) f.d = line_circle(f.r0, f.s, p.radius);
+    else f.d = line_ellipsoid(f.r0, f.s, p.ax);
+    return f.d > 0 && f.d < f.step_l;
 }
 
-// simulations.py:819-875
-template <>
-__device__ __forceinline__ bool walker_step<3>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
-                                               const bool live)
+// specular reflection at the wall f.d ahead (simulations.py:734-741, 793-801, 853-860)
+template <int SUB>
+__device__ __forceinline__ void bounce(Flight &f, const KParams &p)
 {
-    if (!live) return false;
-    Vec3 s = random_step(rng, tab);
-    Vec3 r0 = matvec3(p.R, pos);
-    double step_l = p.step_l;
-    long long iter = 0;
-    bool check = true;
-    while (check && step_l > 0 && iter < p.max_iter) {
-        ++iter;
-        double d = line_ellipsoid(r0, s, p.ax);
-        if (d > 0 && d < step_l) {
-            Vec3 n;
-            n.x = div_(-fma_(d, s.x, r0.x), mul_(p.ax[0], p.ax[0]));
-            n.y = div_(-fma_(d, s.y, r0.y), mul_(p.ax[1], p.ax[1]));
-            n.z = div_(-fma_(d, s.z, r0.z), mul_(p.ax[2], p.ax[2]));
-            n = normalize3(n);
-            reflect(r0, s, d, n, p.eps);
-            step_l = sub_(step_l, add_(d, p.eps));
-        } else {
-            check = false;
+    Vec3 n;
+    if constexpr (SUB == 1) {
+        n.x = -fma_(f.d, f.s.x, f.r0.x);
+        n.y = -fma_(f.d, f.s.y, f.r0.y);
+        n.z = -fma_(f.d, f.s.z, f.r0.z);
+        n = normalize3(n);
+    } else if constexpr (SUB == 2) {
+        double X1 = fma_(f.d, f.s.y, f.r0.y), X2 = fma_(f.d, f.s.z, f.r0.z);
+        double len = sqrt_(fma_(X2, X2, fma_(X1, X1, 0.0)));
+        // normal = (0, -X1, -X2) / len; 0 / len is +0 for every finite positive len
+        double rc = rcp_refined(len);
+        bool ok = len > 0 && div_fast(-X1, len, rc, n.y);
+        ok = ok && div_fast(-X2, len, rc, n.z);
+        n.x = 0.0;
+        if (!ok) {
+            n.x = div_(0.0, len);
+            n.y = div_(-X1, len);
+            n.z = div_(-X2, len);
         }
+    } else {
+        n.x = div_(-fma_(f.d, f.s.x, f.r0.x), mul_(p.ax[0], p.ax[0]));
+        n.y = div_(-fma_(f.d, f.s.y, f.r0.y), mul_(p.ax[1], p.ax[1]));
+        n.z = div_(-fma_(f.d, f.s.z, f.r0.z), mul_(p.ax[2], p.ax[2]));
+        n = normalize3(n);
     }
-    s = matvec3(p.Rinv, s);
-    r0 = matvec3(p.Rinv, r0);
-    pos.x = fma_(step_l, s.x, r0.x);
-    pos.y = fma_(step_l, s.y, r0.y);
-    pos.z = fma_(step_l, s.z, r0.z);
-    return iter >= p.max_iter;
+    reflect(f.r0, f.s, f.d, n, p.eps);
+    f.step_l = sub_(f.step_l, add_(f.d, p.eps));
 }
 
-__device__ __forceinline__ Tri load_tri(const double *tri9, int id)
+// back to the lab frame and the final move (simulations.py:742-745, 802-805, 861-864); returns
+// the iter_exc flag of the step.  The round trip through the substrate frame is kept: its
+// rounding is part of the reference's trajectory.
+template <int SUB>
+__device__ __forceinline__ bool end_step(Vec3 &pos, Flight &f, const KParams &p)
 {
-    const double *q = tri9 + 9ll * id;
+    if constexpr (SUB == 2 || SUB == 3) {
+        f.s = matvec3(p.Rinv, f.s);
+        f.r0 = matvec3(p.Rinv, f.r0);
+    }
+    pos.x = fma_(f.step_l, f.s.x, f.r0.x);
+    pos.y = fma_(f.step_l, f.s.y, f.r0.y);
+    pos.z = fma_(f.step_l, f.s.z, f.r0.z);
+    return f.iter >= p.max_iter;
+}
+
+// simulations.py:705-756 (sphere), :759-816 (cylinder), :819-875 (ellipsoid)
+template <int SUB>
+__device__ __forceinline__ bool walker_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
+                                            const bool live)
+{
+    static_assert(SUB >= 1 && SUB <= 3, "analytic substrates only");
+    if (!live) return false;
+    Flight f;
+    begin_step<SUB>(pos, rng, p, tab, f);
+    while (probe<SUB>(f, p)) bounce<SUB>(f, p);
+    return end_step<SUB>(pos, f, p);
+}
+
+constexpr int kTriStride = 10;  // doubles per triangle record: A, B-A, C-A, pad (five 16-byte loads)
+
+__device__ __forceinline__ Tri load_tri(const double *tri, int id)
+{
+    const double2 *q = reinterpret_cast<const double2 *>(tri + (long long)kTriStride * id);
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4);
     Tri t;
-    t.A.x = __ldg(q + 0); t.A.y = __ldg(q + 1); t.A.z = __ldg(q + 2);
-    t.E1.x = __ldg(q + 3); t.E1.y = __ldg(q + 4); t.E1.z = __ldg(q + 5);
-    t.E2.x = __ldg(q + 6); t.E2.y = __ldg(q + 7); t.E2.z = __ldg(q + 8);
+    t.A.x = a.x; t.A.y = a.y; t.A.z = b.x;
+    t.E1.x = b.y; t.E1.y = c.x; t.E1.z = c.y;
+    t.E2.x = d.x; t.E2.y = d.y; t.E2.z = e.x;
     return t;
 }
 
@@ -245,20 +236,111 @@ __device__ __forceinline__ void axis_cell(const AxisCells &r, int n, long long k
     image = r.nq + (double)q;
 }
 
-constexpr int kCoopCells = 8;  // cells per walker and collision iteration tested cooperatively
+// The common case without divisions and scans: x lies strictly inside a grid cell and its
+// period index is unambiguous.  Then both _ll_ and _ul_subvoxel_overlap_periodic follow from the
+// cell (ll = its global index, ul = that + 1).  Returns false when x is on (or within rounding
+// of) a cell or period boundary; the caller then uses the generic lookups above.
+__device__ __forceinline__ bool cell_of(const double *xs, int n, double V, double invV, double inv_h, double x,
+                                        int &cell, int &image)
+{
+    const double q = x * invV;
+    const double fl = floor(q);
+    const double fr = q - fl;
+    const double sh = fma_(-V, fl, x);  // the reference's xmin_shifted, given floor(x / V) == fl
+    const int c = min(max(__double2int_rz(sh * inv_h), 0), n - 1);
+    const double lo = __ldg(xs + c), hi = __ldg(xs + c + 1);
+    cell = c;
+    image = __double2int_rz(fl);
+    return fr > 1e-9 && fr < 1.0 - 1e-9 && fabs(q) < 1e5 && lo < sh && sh < hi;
+}
 
-// Per-warp scratch: every lane publishes its ray and its short list of grid cells, then the 32
-// lanes share ALL listed (cell, triangle) tests of the warp evenly.
-struct MeshScratch {
-    double ray[6][32];            // position, unit step
-    int begin[kCoopCells][32];    // first entry of the cell in tri_idx
-    int cum[kCoopCells][32];      // inclusive running number of entries over the lane's cells
-    int image[3][kCoopCells][32]; // periodic image number of the cell per axis
+struct AxisSpan {
+    int cell;   // first overlapped cell, index inside the base voxel
+    int image;  // its periodic image number
+    int count;  // cells overlapped (>= 1)
 };
+
+#ifndef DSB_SPAN
+#define DSB_SPAN 3
+#endif
+constexpr int kMaxSpan = DSB_SPAN;  // cells per axis the cooperative search takes
+
+// cells overlapped by [a, b] (a = walker, b = end of the remaining step) along one axis
+__device__ __forceinline__ bool axis_span(const double *xs, int n, double V, double invV, double inv_h, double a,
+                                          double b, AxisSpan &sp)
+{
+    int ca, ia, cb, ib;
+    const bool oka = cell_of(xs, n, V, invV, inv_h, a, ca, ia);
+    const bool okb = cell_of(xs, n, V, invV, inv_h, b, cb, ib);
+    const bool a_first = !(b < a);
+    sp.cell = a_first ? ca : cb;
+    sp.image = a_first ? ia : ib;
+    const long long d = (long long)(ib - ia) * n + (cb - ca);
+    const long long cnt = (a_first ? d : -d) + 1;
+    sp.count = (int)cnt;
+    return oka && okb && cnt >= 1 && cnt <= kMaxSpan && cnt <= n;
+}
+
+constexpr int kSurvivorCap = 256;  // triangles per warp and search that pass the box filter
+constexpr int kRangeCap = 128;     // non-empty cell lists per warp and search
+constexpr int kEntryCap = 4096;    // list entries per warp and search
+constexpr unsigned kSwarH = 0x80008000u;
+
+// Per-warp scratch of the collision search.
+struct MeshScratch {
+    double dir[3][32];     // unit step of each lane's walker
+    double org[3][2][32];  // its position moved into the base voxel: image of the first cell, next image
+    unsigned long long best_d[32];  // closest hit distance per walker (bit pattern of a positive double)
+    unsigned best_key[32];          // visiting-order number of the first triangle at that distance
+    int best_tri[32];               // that triangle
+    uint4 range_box[kRangeCap];     // segment box for the filter (3 words); owner lane | image flags << 8 | order << 16
+    int2 range_pos[kRangeCap];      // number of the range's first entry in the warp's flat numbering; its place in the list
+    unsigned start_bits[kEntryCap / 32];        // bit j: a range starts at flat entry j
+    unsigned long long survivor[kSurvivorCap];  // triangle (32) | owner lane (8) | image flags (3) << 8 | order (16) << 16
+    double hit[kSurvivorCap];                   // distance found for the survivor (inf: none)
+};
+
+// 15-bit grid coordinate of x on an axis of the base voxel (scale = 32767 / xs[-1]); unclamped
+__device__ __forceinline__ int quantize(double x, double scale) { return __double2int_rd(x * scale); }
+__device__ __forceinline__ unsigned clamp15(int q) { return (unsigned)min(max(q, 0), 32767); }
+
+// The cells a walker's remaining segment overlaps, in the reference's visiting order
+// (x -> y -> z): fn(first entry, end entry, image flags) for every cell.
+template <typename Fn>
+__device__ __forceinline__ void for_each_cell(const MeshDev &g, const AxisSpan &sx, const AxisSpan &sy,
+                                              const AxisSpan &sz, Fn fn)
+{
+    for (int ix = 0; ix < sx.count; ++ix) {
+        int cx = sx.cell + ix;
+        const int fx = cx >= g.len_xs - 1;
+        cx -= fx ? g.len_xs - 1 : 0;
+        for (int iy = 0; iy < sy.count; ++iy) {
+            int cy = sy.cell + iy;
+            const int fy = cy >= g.len_ys - 1;
+            cy -= fy ? g.len_ys - 1 : 0;
+            const int2 *row = g.cell_rng + ((long long)cx * g.nsv1 + cy) * g.nsv2;
+            for (int iz = 0; iz < sz.count; ++iz) {
+                int cz = sz.cell + iz;
+                const int fz = cz >= g.len_zs - 1;
+                cz -= fz ? g.len_zs - 1 : 0;
+                const int2 r = __ldg(row + cz);
+                fn(r.x, r.y, fx | (fy << 1) | (fz << 2));
+            }
+        }
+    }
+}
 
 // Closest triangle hit (d > 0) over every triangle listed in the cells the segment
 // [pos, pos + step_l * s] overlaps, visited in the reference's order (cells x -> y -> z, entries
 // ascending, strict "<" so the first minimum wins): simulations.py:936-983.
+//
+// Only hits within the remaining length can change the walk (a larger minimum just ends the
+// collision loop, simulations.py:986), so a triangle whose bounding box does not meet the box of
+// the remaining segment is skipped.  That filter reads a 16-byte record per list entry (triangle
+// id + box on a 15-bit grid, rounded outwards; the segment's box is rounded outwards too, so the
+// filter only ever errs on the side of keeping a triangle).  The lists of all 32 walkers are
+// numbered through and filtered 32 entries at a time (coalesced), the survivors are compacted
+// (ballot) and tested exactly, again 32 at a time.
 __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &sc, const int lane, const bool need,
                                                  const Vec3 &pos, const Vec3 &s, const double step_l,
                                                  double &min_d, int &closest)
@@ -266,122 +348,154 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
     const unsigned full = 0xffffffffu;
     const double inf = __longlong_as_double(0x7FF0000000000000LL);
     min_d = inf;
-    int n_items = 0;
-    bool solo = false;
-    AxisCells ax, ay, az;
+    bool fast = false;
+    AxisSpan sx, sy, sz;
+    double ex = 0.0, ey = 0.0, ez = 0.0;
+    int n_ranges = 0, n_entries = 0;
+    sc.best_d[lane] = 0x7FF0000000000000ULL;
+    sc.best_key[lane] = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < kEntryCap / 1024; ++k) sc.start_bits[lane + 32 * k] = 0u;
     if (need) {
         // end point of the remaining segment: x uses a separately rounded product, y and z are
         // fused (that is how the reference's kernel was compiled)
-        double ex = add_(pos.x, mul_(step_l, s.x));
-        double ey = fma_(step_l, s.y, pos.y);
-        double ez = fma_(step_l, s.z, pos.z);
-        ax = axis_cells(g.xs, g.len_xs, g.vox[0], g.inv_vox[0], g.inv_hx, pos.x, ex);
-        ay = axis_cells(g.ys, g.len_ys, g.vox[1], g.inv_vox[1], g.inv_hy, pos.y, ey);
-        az = axis_cells(g.zs, g.len_zs, g.vox[2], g.inv_vox[2], g.inv_hz, pos.z, ez);
-        if (ax.count > 0 && ay.count > 0 && az.count > 0) {
-            const bool small = ax.count <= kCoopCells && ay.count <= kCoopCells && az.count <= kCoopCells &&
-                               ax.count * ay.count * az.count <= kCoopCells && fabs(ax.nq) < 1e9 &&
-                               fabs(ay.nq) < 1e9 && fabs(az.nq) < 1e9;
-            if (small) {
-                int c = 0;
-                for (int ix = 0; ix < (int)ax.count; ++ix) {
-                    int cx;
-                    double mx;
-                    axis_cell(ax, g.len_xs - 1, ix, cx, mx);
-                    for (int iy = 0; iy < (int)ay.count; ++iy) {
-                        int cy;
-                        double my;
-                        axis_cell(ay, g.len_ys - 1, iy, cy, my);
-                        for (int iz = 0; iz < (int)az.count; ++iz) {
-                            int cz;
-                            double mz;
-                            axis_cell(az, g.len_zs - 1, iz, cz, mz);
-                            int2 r = __ldg(g.cell_rng + ((long long)cx * g.nsv1 + cy) * g.nsv2 + cz);
-                            n_items += r.y - r.x;
-                            sc.begin[c][lane] = r.x;
-                            sc.cum[c][lane] = n_items;
-                            sc.image[0][c][lane] = (int)mx;
-                            sc.image[1][c][lane] = (int)my;
-                            sc.image[2][c][lane] = (int)mz;
-                            ++c;
-                        }
-                    }
-                }
-                sc.ray[0][lane] = pos.x; sc.ray[1][lane] = pos.y; sc.ray[2][lane] = pos.z;
-                sc.ray[3][lane] = s.x; sc.ray[4][lane] = s.y; sc.ray[5][lane] = s.z;
-            } else {
-                solo = true;
-            }
-        }
+        ex = add_(pos.x, mul_(step_l, s.x));
+        ey = fma_(step_l, s.y, pos.y);
+        ez = fma_(step_l, s.z, pos.z);
+        fast = axis_span(g.xs, g.len_xs - 1, g.vox[0], g.inv_vox[0], g.inv_hx, pos.x, ex, sx);
+        fast &= axis_span(g.ys, g.len_ys - 1, g.vox[1], g.inv_vox[1], g.inv_hy, pos.y, ey, sy);
+        fast &= axis_span(g.zs, g.len_zs - 1, g.vox[2], g.inv_vox[2], g.inv_hz, pos.z, ez, sz);
+        if (fast)
+            for_each_cell(g, sx, sy, sz, [&](int b, int e, int) {
+                n_ranges += e > b;
+                n_entries += e - b;
+            });
     }
-    __syncwarp();
-
-    // exclusive prefix sum of the lanes' item counts
-    int incl = n_items;
+    // this lane's place in the warp's numbering of ranges and entries
+    int incl_r = n_ranges, incl_e = n_entries;
 #pragma unroll
     for (int st = 1; st < 32; st <<= 1) {
-        int v = __shfl_up_sync(full, incl, st);
-        if (lane >= st) incl += v;
+        const int vr = __shfl_up_sync(full, incl_r, st), ve = __shfl_up_sync(full, incl_e, st);
+        if (lane >= st) {
+            incl_r += vr;
+            incl_e += ve;
+        }
     }
-    const int excl = incl - n_items;
-    const int total = __shfl_sync(full, incl, 31);
-
-    for (int base = 0; base < total; base += 32) {
-        const int j = base + lane;
-        // owner = last lane whose first item index is <= j
-        int owner = 0;
-#pragma unroll
-        for (int st = 16; st > 0; st >>= 1) {
-            int cand = owner + st;
-            int first = __shfl_sync(full, excl, cand & 31);
-            if (cand < 32 && first <= j) owner = cand;
-        }
-        const int owner_first = __shfl_sync(full, excl, owner);
-        double d = inf;
-        int id = -1;
-        if (j < total) {
-            const int i = j - owner_first;
-            int c = 0;
-            while (i >= sc.cum[c][owner]) ++c;
-            const int entry = sc.begin[c][owner] + i - (c ? sc.cum[c - 1][owner] : 0);
-            id = __ldg(g.tri_idx + entry);
-            const Tri tr = load_tri(g.tri9, id);
-            const int mx = sc.image[0][c][owner], my = sc.image[1][c][owner], mz = sc.image[2][c][owner];
-            Vec3 o, dir;
-            // walker moved into the base voxel: r0 - shift_n * xs[-1] (simulations.py:943, 970-971)
-            o.x = sub_(sc.ray[0][owner], mx == 0 ? 0.0 : mul_((double)mx, g.top[0]));
-            o.y = sub_(sc.ray[1][owner], my == 0 ? 0.0 : mul_((double)my, g.top[1]));
-            o.z = sub_(sc.ray[2][owner], mz == 0 ? 0.0 : mul_((double)mz, g.top[2]));
-            dir.x = sc.ray[3][owner]; dir.y = sc.ray[4][owner]; dir.z = sc.ray[5][owner];
-            const double t = ray_triangle(tr, o, dir);
-            if (t > 0) d = t;
-        }
-        // segmented running minimum over lanes that serve the same owner; on ties the earlier
-        // item (lower lane) wins, like the reference's strict "<" in visiting order
-#pragma unroll
-        for (int st = 1; st < 32; st <<= 1) {
-            double dp = __shfl_up_sync(full, d, st);
-            int ip = __shfl_up_sync(full, id, st);
-            int op = __shfl_up_sync(full, owner, st);
-            if (lane >= st && op == owner && dp <= d) {
-                d = dp;
-                id = ip;
+    // walkers past the tables' capacity search alone (they form a suffix of the lanes)
+    const bool coop = fast && incl_r <= kRangeCap && incl_e <= kEntryCap;
+    const int total = __reduce_max_sync(full, coop ? incl_e : 0);
+    __syncwarp();
+    if (coop && n_entries > 0) {
+        sc.dir[0][lane] = s.x; sc.dir[1][lane] = s.y; sc.dir[2][lane] = s.z;
+        // walker moved into the base voxel: r0 - shift_n * xs[-1] (simulations.py:943, 970-971)
+        const double ox = sub_(pos.x, mul_((double)sx.image, g.top[0]));
+        const double oy = sub_(pos.y, mul_((double)sy.image, g.top[1]));
+        const double oz = sub_(pos.z, mul_((double)sz.image, g.top[2]));
+        sc.org[0][0][lane] = ox;
+        sc.org[1][0][lane] = oy;
+        sc.org[2][0][lane] = oz;
+        sc.org[0][1][lane] = sub_(pos.x, mul_((double)(sx.image + 1), g.top[0]));
+        sc.org[1][1][lane] = sub_(pos.y, mul_((double)(sy.image + 1), g.top[1]));
+        sc.org[2][1][lane] = sub_(pos.z, mul_((double)(sz.image + 1), g.top[2]));
+        // box of the remaining segment on the 15-bit grid, padded by a thousandth of its length
+        // and two grid units; in the next image every coordinate is one period (32767) lower
+        const double pad = 1e-3 * step_l;
+        const double dx = step_l * s.x, dy = step_l * s.y, dz = step_l * s.z;
+        const int lox = quantize(ox + fmin(dx, 0.0) - pad, g.qscale[0]) - 2, hix = quantize(ox + fmax(dx, 0.0) + pad, g.qscale[0]) + 3;
+        const int loy = quantize(oy + fmin(dy, 0.0) - pad, g.qscale[1]) - 2, hiy = quantize(oy + fmax(dy, 0.0) + pad, g.qscale[1]) + 3;
+        const int loz = quantize(oz + fmin(dz, 0.0) - pad, g.qscale[2]) - 2, hiz = quantize(oz + fmax(dz, 0.0) + pad, g.qscale[2]) + 3;
+        int k = incl_r - n_ranges, first = incl_e - n_entries, order = 0;
+        for_each_cell(g, sx, sy, sz, [&](int b, int e, int flags) {
+            if (e > b) {
+                const int fx = flags & 1, fy = (flags >> 1) & 1, fz = flags >> 2;
+                const unsigned bhx = clamp15(hix - 32767 * fx), blx = 32767u - clamp15(lox - 32767 * fx);
+                const unsigned bhy = clamp15(hiy - 32767 * fy), bly = 32767u - clamp15(loy - 32767 * fy);
+                const unsigned bhz = clamp15(hiz - 32767 * fz), blz = 32767u - clamp15(loz - 32767 * fz);
+                // triangle box (lo, 32767 - hi) <= these, halfword by halfword  <=>  the boxes meet
+                sc.range_box[k] = make_uint4((bhx | (bhy << 16)) + kSwarH, (bhz | (blx << 16)) + kSwarH,
+                                             (bly | (blz << 16)) + kSwarH,
+                                             (unsigned)lane | ((unsigned)flags << 8) | ((unsigned)order << 16));
+                sc.range_pos[k] = make_int2(first, b);
+                atomicOr(&sc.start_bits[first >> 5], 1u << (first & 31));
+                ++k;
+                first += e - b;
+                order += e - b;
             }
-        }
-        // every owner with items in this round takes the result of its segment's last lane
-        const int lo = max(excl, base), hi = min(excl + n_items, base + 32);
-        const bool mine = lo < hi;
-        const int src = mine ? hi - 1 - base : lane;
-        const double ds = __shfl_sync(full, d, src);
-        const int is = __shfl_sync(full, id, src);
-        if (mine && ds < min_d) {
-            min_d = ds;
-            closest = is;
-        }
+        });
     }
     __syncwarp();
 
-    if (solo) {  // more cells than the shared table holds: this lane walks its own cells
+    // box filter over the warp's entries, 32 at a time
+    int n_surv = 0, started = 0;  // warp-uniform: survivors so far, ranges that start before this round
+    for (int j0 = 0; j0 < total; j0 += 32) {
+        const unsigned starts = sc.start_bits[j0 >> 5];
+        const int j = j0 + lane;
+        bool pass = false;
+        unsigned long long rec = 0ull;
+        if (j < total) {
+            const int r = started + __popc(starts & (0xffffffffu >> (31 - lane))) - 1;
+            const uint4 a = sc.range_box[r];
+            const int2 rp = sc.range_pos[r];
+            const uint4 b = __ldg(g.entry + rp.y + (j - rp.x));
+            pass = ((a.x - b.y) & (a.y - b.z) & (a.z - b.w) & kSwarH) == kSwarH;
+            rec = (unsigned long long)b.x | ((unsigned long long)(a.w + ((unsigned)(j - rp.x) << 16)) << 32);
+        }
+        const unsigned m = __ballot_sync(full, pass);
+        if (pass) {
+            const int k = n_surv + __popc(m & ((1u << lane) - 1u));
+            if (k < kSurvivorCap) sc.survivor[k] = rec;
+        }
+        n_surv += __popc(m);
+        started += __popc(starts);
+    }
+    const bool overflow = n_surv > kSurvivorCap;  // every walker of the warp then searches alone
+    n_surv = overflow ? 0 : n_surv;
+    __syncwarp();
+
+    // exact tests of the survivors, 32 at a time
+    for (int j = lane; j < n_surv; j += 32) {
+        const unsigned long long w = sc.survivor[j];
+        const unsigned hi = (unsigned)(w >> 32);
+        const int owner = hi & 0xff, flags = (hi >> 8) & 7;
+        Vec3 o, dir;
+        o.x = sc.org[0][flags & 1][owner];
+        o.y = sc.org[1][(flags >> 1) & 1][owner];
+        o.z = sc.org[2][(flags >> 2) & 1][owner];
+        dir.x = sc.dir[0][owner]; dir.y = sc.dir[1][owner]; dir.z = sc.dir[2][owner];
+        const double t = ray_triangle(load_tri(g.tri, (int)(unsigned)w), o, dir);
+        const bool is_hit = t > 0;
+        sc.hit[j] = is_hit ? t : inf;
+        if (is_hit) atomicMin(&sc.best_d[owner], (unsigned long long)__double_as_longlong(t));
+    }
+    __syncwarp();
+    // equal distances (a ray through a shared edge): the triangle visited first wins
+    for (int j = lane; j < n_surv; j += 32) {
+        const unsigned hi = (unsigned)(sc.survivor[j] >> 32);
+        const double t = sc.hit[j];
+        if (t < inf && (unsigned long long)__double_as_longlong(t) == sc.best_d[hi & 0xff])
+            atomicMin(&sc.best_key[hi & 0xff], hi >> 16);
+    }
+    __syncwarp();
+    for (int j = lane; j < n_surv; j += 32) {
+        const unsigned long long w = sc.survivor[j];
+        const unsigned hi = (unsigned)(w >> 32);
+        const double t = sc.hit[j];
+        if (t < inf && (unsigned long long)__double_as_longlong(t) == sc.best_d[hi & 0xff] &&
+            (hi >> 16) == sc.best_key[hi & 0xff])
+            sc.best_tri[hi & 0xff] = (int)(unsigned)w;
+    }
+    __syncwarp();
+
+    if (coop && !overflow) {
+        const double d = __longlong_as_double((long long)sc.best_d[lane]);
+        if (d < inf) {
+            min_d = d;
+            closest = sc.best_tri[lane];
+        }
+    } else if (need) {  // boundary cases, long segments, table overflow: this lane walks its own cells
+        const AxisCells ax = axis_cells(g.xs, g.len_xs, g.vox[0], g.inv_vox[0], g.inv_hx, pos.x, ex);
+        const AxisCells ay = axis_cells(g.ys, g.len_ys, g.vox[1], g.inv_vox[1], g.inv_hy, pos.y, ey);
+        const AxisCells az = axis_cells(g.zs, g.len_zs, g.vox[2], g.inv_vox[2], g.inv_hz, pos.z, ez);
         for (long long ix = 0; ix < ax.count; ++ix) {
             int cx;
             double mx;
@@ -401,7 +515,7 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
                     const int2 r = __ldg(g.cell_rng + ((long long)cx * g.nsv1 + cy) * g.nsv2 + cz);
                     for (int i = r.x; i < r.y; ++i) {
                         const int id = __ldg(g.tri_idx + i);
-                        const double d = ray_triangle(load_tri(g.tri9, id), tr0, s);
+                        const double d = ray_triangle(load_tri(g.tri, id), tr0, s);
                         if (d > 0 && d < min_d) {
                             closest = id;
                             min_d = d;
@@ -415,17 +529,16 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
 
 // simulations.py:878-1013.  Warp-synchronous: every lane of the warp must call it (live == false
 // for lanes without a walker); the collision search of each iteration is shared by the warp.
-template <>
-__device__ __forceinline__ bool walker_step<4>(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
-                                               const bool live)
+__device__ __forceinline__ bool mesh_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab, const bool live)
 {
     __shared__ MeshScratch s_scratch[kBlock / 32];
     MeshScratch &sc = s_scratch[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const MeshDev &g = p.mesh;
+    __syncwarp();  // lanes leave the previous step's collision loop at different times
     Vec3 s = random_step(rng, tab);
     double step_l = p.step_l;
-    long long iter = 0;
+    int iter = 0;
     bool check = live;
     int closest = 0;
     for (;;) {
@@ -439,7 +552,7 @@ __device__ __forceinline__ bool walker_step<4>(Vec3 &pos, Rng &rng, const KParam
                 check = false;
             } else {
                 double u = u01_f64(rng_next(rng));
-                Vec3 n = triangle_normal(load_tri(g.tri9, closest));
+                Vec3 n = triangle_normal(load_tri(g.tri, closest));
                 if (g.perm_prob < u)
                     reflect(pos, s, min_d, n, p.eps);
                 else
@@ -494,6 +607,19 @@ __device__ __forceinline__ void block_signal(const KParams &p, bool valid, Phase
 
 // ---------------------------------------------------------------- the walk kernel
 
+template <int SUB>
+__device__ __forceinline__ bool time_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab, const bool live)
+{
+    if constexpr (SUB == 0) return free_step(pos, rng, p, tab, live);
+    else if constexpr (SUB == 4) return mesh_step(pos, rng, p, tab, live);
+    else return walker_step<SUB>(pos, rng, p, tab, live);
+}
+
+#ifndef DSB_PARK
+#define DSB_PARK 4
+#endif
+constexpr int kParkFlush = DSB_PARK;  // parked walkers per warp that trigger a bounce pass
+
 // MR > 0: n_meas == MR phases in registers.  MR == 0: any n_meas; positions of kTimeChunk steps
 // are buffered in registers, then each measurement's phase makes one round trip through its
 // (coalesced, L2-resident) row of `phases` per chunk instead of one per step.
@@ -523,14 +649,55 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : DSB_M
         double ph[MR];
 #pragma unroll
         for (int m = 0; m < MR; ++m) ph[m] = (active && p.t0 > 0) ? p.phases[(long long)m * N + w] : 0.0;
-        // the time loop is uniform over the block (the mesh step shares work inside each warp)
-        for (int t = p.t0; t < p.t1; ++t) {
-            exc |= walker_step<SUB>(pos, rng, p, s_tab, active);
+        // phase accumulation with the post-step position (simulations.py:746-755 and alike)
+        auto accumulate = [&](int t) {
 #pragma unroll
             for (int m = 0; m < MR; ++m) {
                 const double *g = p.grad + ((long long)m * p.n_t + t) * 3;
                 double gx = __ldg(g), gy = __ldg(g + 1), gz = __ldg(g + 2);
                 ph[m] = fma_(p.gamma_dt, fma_(gz, pos.z, fma_(gx, pos.x, mul_(gy, pos.y))), ph[m]);
+            }
+        };
+        if constexpr (SUB >= 1 && SUB <= 3 && kParkFlush > 1) {
+            // Collisions are rare per walker and step but not per warp: taken inline, the
+            // reflection code would run for one or two lanes in most steps of every warp.  So
+            // the lanes of a warp are not kept in lock step: a walker that hits the wall is
+            // parked with its step in flight while the other lanes go on with their next steps,
+            // and once kParkFlush walkers of the warp are parked (ballot) they are bounced
+            // together.  Every walker still executes exactly its own sequence of operations,
+            // so results do not depend on the grouping.
+            const unsigned full = 0xffffffffu;
+            int t = p.t0;
+            bool parked = false;
+            Flight f;
+            f.d = 0.0;
+            for (;;) {
+                const bool fresh = active && !parked && t < p.t1;
+                const unsigned m_parked = __ballot_sync(full, parked);
+                const unsigned m_fresh = __ballot_sync(full, fresh);
+                if ((m_parked | m_fresh) == 0) break;
+                bool moved;
+                if (__popc(m_parked) >= kParkFlush || m_fresh == 0) {
+                    moved = parked;
+                    if (parked) bounce<SUB>(f, p);
+                } else {
+                    moved = fresh;
+                    if (fresh) begin_step<SUB>(pos, rng, p, s_tab, f);
+                }
+                if (moved) {
+                    parked = probe<SUB>(f, p);
+                    if (!parked) {
+                        exc |= end_step<SUB>(pos, f, p);
+                        accumulate(t);
+                        ++t;
+                    }
+                }
+            }
+        } else {
+            // the time loop is uniform over the block (the mesh step shares work inside each warp)
+            for (int t = p.t0; t < p.t1; ++t) {
+                exc |= time_step<SUB>(pos, rng, p, s_tab, active);
+                accumulate(t);
             }
         }
         if (active) {
@@ -558,7 +725,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : DSB_M
 #pragma unroll
             for (int k = 0; k < kTimeChunk; ++k)
                 if (k < cnt) {
-                    exc |= walker_step<SUB>(pos, rng, p, s_tab, active);
+                    exc |= time_step<SUB>(pos, rng, p, s_tab, active);
                     buf[k] = pos;
                 }
             if (active)
