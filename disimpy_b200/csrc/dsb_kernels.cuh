@@ -527,8 +527,22 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
     }
 }
 
-// simulations.py:878-1013.  Warp-synchronous: every lane of the warp must call it (live == false
-// for lanes without a walker); the collision search of each iteration is shared by the warp.
+// What happens at the closest triangle (simulations.py:986-997): one uniform draw (also when
+// perm_prob == 0), then reflection or passage through the membrane.
+__device__ __forceinline__ void mesh_collision(const MeshDev &g, Vec3 &pos, Vec3 &s, Rng &rng, double min_d,
+                                               int closest, double eps)
+{
+    const double u = u01_f64(rng_next(rng));
+    const Vec3 n = triangle_normal(load_tri(g.tri, closest));
+    if (g.perm_prob < u)
+        reflect(pos, s, min_d, n, eps);
+    else
+        cross_membrane(pos, s, min_d, n, eps);
+}
+
+// simulations.py:878-1013, one whole time step.  Warp-synchronous: every lane of the warp must
+// call it (live == false for lanes without a walker); the collision search of each iteration is
+// shared by the warp.
 __device__ __forceinline__ bool mesh_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab, const bool live)
 {
     __shared__ MeshScratch s_scratch[kBlock / 32];
@@ -551,12 +565,7 @@ __device__ __forceinline__ bool mesh_step(Vec3 &pos, Rng &rng, const KParams &p,
             if (min_d > step_l) {
                 check = false;
             } else {
-                double u = u01_f64(rng_next(rng));
-                Vec3 n = triangle_normal(load_tri(g.tri, closest));
-                if (g.perm_prob < u)
-                    reflect(pos, s, min_d, n, p.eps);
-                else
-                    cross_membrane(pos, s, min_d, n, p.eps);
+                mesh_collision(g, pos, s, rng, min_d, closest, p.eps);
                 step_l = sub_(step_l, min_d);
             }
         }
@@ -693,8 +702,51 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : DSB_M
                     }
                 }
             }
+        } else if constexpr (SUB == 4) {
+            // The collision search is shared by the warp (mesh_closest_hit), so a second search
+            // for the one or two walkers that bounced costs about as much as the first one for
+            // all 32.  The lanes are therefore not kept in lock step: a walker that bounced stays
+            // in flight and takes part in the warp's next search together with the other lanes'
+            // next time steps.  Every walker still executes exactly its own sequence of
+            // operations (simulations.py:878-1013).
+            __shared__ MeshScratch s_scratch[kBlock / 32];
+            MeshScratch &sc = s_scratch[threadIdx.x >> 5];
+            const int lane = threadIdx.x & 31;
+            const MeshDev &g = p.mesh;
+            int t = p.t0, iter = 0, closest = 0;
+            bool in_flight = false;
+            Vec3 s = {0.0, 0.0, 0.0};
+            double step_l = 0.0;
+            for (;;) {
+                const bool fresh = active && !in_flight && t < p.t1;
+                if (!__any_sync(0xffffffffu, fresh || in_flight)) break;
+                if (fresh) {
+                    s = random_step(rng, s_tab);
+                    step_l = p.step_l;
+                    iter = 0;
+                    in_flight = true;
+                }
+                const bool need = in_flight && step_l > 0 && iter < p.max_iter;
+                if (need) ++iter;
+                double min_d;
+                mesh_closest_hit(g, sc, lane, need, pos, s, step_l, min_d, closest);
+                if (in_flight) {
+                    if (need && !(min_d > step_l)) {
+                        mesh_collision(g, pos, s, rng, min_d, closest, p.eps);
+                        step_l = sub_(step_l, min_d);
+                    } else {
+                        pos.x = fma_(step_l, s.x, pos.x);
+                        pos.y = fma_(step_l, s.y, pos.y);
+                        pos.z = fma_(step_l, s.z, pos.z);
+                        exc |= iter >= p.max_iter;
+                        accumulate(t);
+                        ++t;
+                        in_flight = false;
+                    }
+                }
+            }
         } else {
-            // the time loop is uniform over the block (the mesh step shares work inside each warp)
+            // the time loop is uniform over the block
             for (int t = p.t0; t < p.t1; ++t) {
                 exc |= time_step<SUB>(pos, rng, p, s_tab, active);
                 accumulate(t);
