@@ -295,7 +295,7 @@ struct MeshScratch {
     int best_tri[32];               // that triangle
     uint4 range_box[kRangeCap];     // segment box for the filter (3 words); owner lane | image flags << 8 | order << 16
     int2 range_pos[kRangeCap];      // number of the range's first entry in the warp's flat numbering; its place in the list
-    unsigned start_bits[kEntryCap / 32];        // bit j: a range starts at flat entry j
+    unsigned start_bits[kEntryCap / 32 + 1];    // bit j: a range starts at flat entry j (+ a word of padding)
     unsigned long long survivor[kSurvivorCap];  // triangle (32) | owner lane (8) | image flags (3) << 8 | order (16) << 16
     double hit[kSurvivorCap];                   // distance found for the survivor (inf: none)
 };
@@ -304,31 +304,32 @@ struct MeshScratch {
 __device__ __forceinline__ int quantize(double x, double scale) { return __double2int_rd(x * scale); }
 __device__ __forceinline__ unsigned clamp15(int q) { return (unsigned)min(max(q, 0), 32767); }
 
-// The cells a walker's remaining segment overlaps, in the reference's visiting order
-// (x -> y -> z): fn(first entry, end entry, image flags) for every cell.
-template <typename Fn>
-__device__ __forceinline__ void for_each_cell(const MeshDev &g, const AxisSpan &sx, const AxisSpan &sy,
-                                              const AxisSpan &sz, Fn fn)
-{
-    for (int ix = 0; ix < sx.count; ++ix) {
-        int cx = sx.cell + ix;
-        const int fx = cx >= g.len_xs - 1;
-        cx -= fx ? g.len_xs - 1 : 0;
-        for (int iy = 0; iy < sy.count; ++iy) {
-            int cy = sy.cell + iy;
-            const int fy = cy >= g.len_ys - 1;
-            cy -= fy ? g.len_ys - 1 : 0;
-            const int2 *row = g.cell_rng + ((long long)cx * g.nsv1 + cy) * g.nsv2;
-            for (int iz = 0; iz < sz.count; ++iz) {
-                int cz = sz.cell + iz;
-                const int fz = cz >= g.len_zs - 1;
-                cz -= fz ? g.len_zs - 1 : 0;
-                const int2 r = __ldg(row + cz);
-                fn(r.x, r.y, fx | (fy << 1) | (fz << 2));
-            }
-        }
+constexpr int kMaxCells = 12;  // cells per walker and search the cooperative path takes
+
+// c-th cell (visiting order x -> y -> z) of the spans: place of its list range, image flags
+struct CellWalk {
+    int ix = 0, iy = 0, iz = 0;
+    __device__ __forceinline__ void next(const AxisSpan &sy, const AxisSpan &sz)
+    {
+        const bool wz = ++iz == sz.count;
+        iz = wz ? 0 : iz;
+        iy += wz;
+        const bool wy = iy == sy.count;
+        iy = wy ? 0 : iy;
+        ix += wy;
     }
-}
+    __device__ __forceinline__ int index(const MeshDev &g, const AxisSpan &sx, const AxisSpan &sy, const AxisSpan &sz,
+                                         int &flags) const
+    {
+        int cx = sx.cell + ix, cy = sy.cell + iy, cz = sz.cell + iz;
+        const int fx = cx >= g.len_xs - 1, fy = cy >= g.len_ys - 1, fz = cz >= g.len_zs - 1;
+        cx -= fx ? g.len_xs - 1 : 0;
+        cy -= fy ? g.len_ys - 1 : 0;
+        cz -= fz ? g.len_zs - 1 : 0;
+        flags = fx | (fy << 1) | (fz << 2);
+        return (cx * g.nsv1 + cy) * g.nsv2 + cz;
+    }
+};
 
 // Closest triangle hit (d > 0) over every triangle listed in the cells the segment
 // [pos, pos + step_l * s] overlaps, visited in the reference's order (cells x -> y -> z, entries
@@ -349,9 +350,9 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
     const double inf = __longlong_as_double(0x7FF0000000000000LL);
     min_d = inf;
     bool fast = false;
-    AxisSpan sx, sy, sz;
+    AxisSpan sx = {0, 0, 0}, sy = {0, 0, 0}, sz = {0, 0, 0};
     double ex = 0.0, ey = 0.0, ez = 0.0;
-    int n_ranges = 0, n_entries = 0;
+    int n_ranges = 0, n_entries = 0, n_cells = 0;
     sc.best_d[lane] = 0x7FF0000000000000ULL;
     sc.best_key[lane] = 0xffffffffu;
 #pragma unroll
@@ -365,11 +366,27 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         fast = axis_span(g.xs, g.len_xs - 1, g.vox[0], g.inv_vox[0], g.inv_hx, pos.x, ex, sx);
         fast &= axis_span(g.ys, g.len_ys - 1, g.vox[1], g.inv_vox[1], g.inv_hy, pos.y, ey, sy);
         fast &= axis_span(g.zs, g.len_zs - 1, g.vox[2], g.inv_vox[2], g.inv_hz, pos.z, ez, sz);
-        if (fast)
-            for_each_cell(g, sx, sy, sz, [&](int b, int e, int) {
-                n_ranges += e > b;
-                n_entries += e - b;
-            });
+        n_cells = sx.count * sy.count * sz.count;
+        fast = fast && n_cells <= kMaxCells;
+    }
+    // list ranges of this lane's cells: independent loads, all in flight together
+    int2 rng[kMaxCells];
+    {
+        CellWalk cw;
+#pragma unroll
+        for (int c = 0; c < kMaxCells; ++c) {
+            rng[c] = make_int2(0, 0);
+            if (fast && c < n_cells) {
+                int flags;
+                rng[c] = __ldg(g.cell_rng + cw.index(g, sx, sy, sz, flags));
+            }
+            cw.next(sy, sz);
+        }
+#pragma unroll
+        for (int c = 0; c < kMaxCells; ++c) {
+            n_ranges += rng[c].y > rng[c].x;
+            n_entries += rng[c].y - rng[c].x;
+        }
     }
     // this lane's place in the warp's numbering of ranges and entries
     int incl_r = n_ranges, incl_e = n_entries;
@@ -404,49 +421,69 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         const int lox = quantize(ox + fmin(dx, 0.0) - pad, g.qscale[0]) - 2, hix = quantize(ox + fmax(dx, 0.0) + pad, g.qscale[0]) + 3;
         const int loy = quantize(oy + fmin(dy, 0.0) - pad, g.qscale[1]) - 2, hiy = quantize(oy + fmax(dy, 0.0) + pad, g.qscale[1]) + 3;
         const int loz = quantize(oz + fmin(dz, 0.0) - pad, g.qscale[2]) - 2, hiz = quantize(oz + fmax(dz, 0.0) + pad, g.qscale[2]) + 3;
-        int k = incl_r - n_ranges, first = incl_e - n_entries, order = 0;
-        for_each_cell(g, sx, sy, sz, [&](int b, int e, int flags) {
-            if (e > b) {
+        const unsigned hx[2] = {clamp15(hix), clamp15(hix - 32767)}, lx[2] = {32767u - clamp15(lox), 32767u - clamp15(lox - 32767)};
+        const unsigned hy[2] = {clamp15(hiy), clamp15(hiy - 32767)}, ly[2] = {32767u - clamp15(loy), 32767u - clamp15(loy - 32767)};
+        const unsigned hz[2] = {clamp15(hiz), clamp15(hiz - 32767)}, lz[2] = {32767u - clamp15(loz), 32767u - clamp15(loz - 32767)};
+        int k = incl_r - n_ranges, first = incl_e - n_entries;
+        CellWalk cw;
+#pragma unroll
+        for (int c = 0; c < kMaxCells; ++c) {
+            const int n = rng[c].y - rng[c].x;
+            if (n > 0) {
+                int flags;
+                cw.index(g, sx, sy, sz, flags);
                 const int fx = flags & 1, fy = (flags >> 1) & 1, fz = flags >> 2;
-                const unsigned bhx = clamp15(hix - 32767 * fx), blx = 32767u - clamp15(lox - 32767 * fx);
-                const unsigned bhy = clamp15(hiy - 32767 * fy), bly = 32767u - clamp15(loy - 32767 * fy);
-                const unsigned bhz = clamp15(hiz - 32767 * fz), blz = 32767u - clamp15(loz - 32767 * fz);
                 // triangle box (lo, 32767 - hi) <= these, halfword by halfword  <=>  the boxes meet
-                sc.range_box[k] = make_uint4((bhx | (bhy << 16)) + kSwarH, (bhz | (blx << 16)) + kSwarH,
-                                             (bly | (blz << 16)) + kSwarH,
-                                             (unsigned)lane | ((unsigned)flags << 8) | ((unsigned)order << 16));
-                sc.range_pos[k] = make_int2(first, b);
+                sc.range_box[k] = make_uint4(((fx ? hx[1] : hx[0]) | ((fy ? hy[1] : hy[0]) << 16)) + kSwarH,
+                                             ((fz ? hz[1] : hz[0]) | ((fx ? lx[1] : lx[0]) << 16)) + kSwarH,
+                                             ((fy ? ly[1] : ly[0]) | ((fz ? lz[1] : lz[0]) << 16)) + kSwarH,
+                                             (unsigned)lane | ((unsigned)flags << 8) |
+                                                 ((unsigned)(first - (incl_e - n_entries)) << 16));
+                sc.range_pos[k] = make_int2(first, rng[c].x);
                 atomicOr(&sc.start_bits[first >> 5], 1u << (first & 31));
                 ++k;
-                first += e - b;
-                order += e - b;
+                first += n;
             }
-        });
+            cw.next(sy, sz);
+        }
     }
     __syncwarp();
 
-    // box filter over the warp's entries, 32 at a time
+    // box filter over the warp's entries, 2 x 32 per iteration (two independent loads in flight)
     int n_surv = 0, started = 0;  // warp-uniform: survivors so far, ranges that start before this round
-    for (int j0 = 0; j0 < total; j0 += 32) {
-        const unsigned starts = sc.start_bits[j0 >> 5];
-        const int j = j0 + lane;
-        bool pass = false;
-        unsigned long long rec = 0ull;
-        if (j < total) {
-            const int r = started + __popc(starts & (0xffffffffu >> (31 - lane))) - 1;
-            const uint4 a = sc.range_box[r];
-            const int2 rp = sc.range_pos[r];
-            const uint4 b = __ldg(g.entry + rp.y + (j - rp.x));
-            pass = ((a.x - b.y) & (a.y - b.z) & (a.z - b.w) & kSwarH) == kSwarH;
-            rec = (unsigned long long)b.x | ((unsigned long long)(a.w + ((unsigned)(j - rp.x) << 16)) << 32);
+    for (int j0 = 0; j0 < total; j0 += 64) {
+        const unsigned starts0 = sc.start_bits[j0 >> 5], starts1 = sc.start_bits[(j0 >> 5) + 1];
+        const int started1 = started + __popc(starts0);
+        bool pass[2] = {false, false};
+        unsigned long long rec[2] = {0ull, 0ull};
+        uint4 a[2], b[2];
+        int off[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = j0 + 32 * h + lane;
+            a[h] = make_uint4(0u, 0u, 0u, 0u);
+            b[h] = make_uint4(0u, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            off[h] = 0;
+            if (j < total) {
+                const int r = (h ? started1 : started) + __popc((h ? starts1 : starts0) & (0xffffffffu >> (31 - lane))) - 1;
+                a[h] = sc.range_box[r];
+                const int2 rp = sc.range_pos[r];
+                off[h] = j - rp.x;
+                b[h] = __ldg(g.entry + rp.y + off[h]);
+            }
         }
-        const unsigned m = __ballot_sync(full, pass);
-        if (pass) {
-            const int k = n_surv + __popc(m & ((1u << lane) - 1u));
-            if (k < kSurvivorCap) sc.survivor[k] = rec;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            pass[h] = ((a[h].x - b[h].y) & (a[h].y - b[h].z) & (a[h].z - b[h].w) & kSwarH) == kSwarH;
+            rec[h] = (unsigned long long)b[h].x | ((unsigned long long)(a[h].w + ((unsigned)off[h] << 16)) << 32);
+            const unsigned m = __ballot_sync(full, pass[h]);
+            if (pass[h]) {
+                const int k = n_surv + __popc(m & ((1u << lane) - 1u));
+                if (k < kSurvivorCap) sc.survivor[k] = rec[h];
+            }
+            n_surv += __popc(m);
         }
-        n_surv += __popc(m);
-        started += __popc(starts);
+        started = started1 + __popc(starts1);
     }
     const bool overflow = n_surv > kSurvivorCap;  // every walker of the warp then searches alone
     n_surv = overflow ? 0 : n_surv;

@@ -5,4 +5,4 @@ for v in ""; do
 done
 unset DISIMPY_B200_LIB
 export KBENCH_NT=300
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:walk_kernel -s 1 -c 1 -f -o gpurun_out/prof_r01_mesh_g python tools/kbench.py mesh 2>&1 | tail -3
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:walk_kernel -s 1 -c 1 -f -o gpurun_out/prof_r01_mesh_h python tools/kbench.py mesh 2>&1 | tail -3
