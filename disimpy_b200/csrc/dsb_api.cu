@@ -270,7 +270,7 @@ struct dsb_sim {
     dsb_params prm{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double *d_grad = nullptr, *d_pos = nullptr, *d_phases = nullptr, *d_partials = nullptr, *d_signal = nullptr;
+    double *d_grad = nullptr, *d_grad_chunked = nullptr, *d_pos = nullptr, *d_phases = nullptr, *d_partials = nullptr, *d_signal = nullptr;
     unsigned long long *d_rng = nullptr, *d_rng0 = nullptr;
     unsigned char *d_exc = nullptr;
     MeshBuffers mesh;
@@ -356,6 +356,7 @@ int dsb_destroy(dsb_sim *s)
     if (s->timer0) cudaEventDestroy(s->timer0);
     if (s->timer1) cudaEventDestroy(s->timer1);
     cudaFree(s->d_grad);
+    cudaFree(s->d_grad_chunked);
     cudaFree(s->d_pos);
     cudaFree(s->d_phases);
     cudaFree(s->d_partials);
@@ -405,6 +406,16 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
     DSB_TRY(cudaMalloc(&s->d_rng0, sizeof(unsigned long long) * 2 * N));
     DSB_TRY(cudaMalloc(&s->d_exc, N));
     DSB_TRY(cudaMemcpyAsync(s->d_grad, gradient, sizeof(double) * 3 * M * T, cudaMemcpyHostToDevice, s->stream));
+    if (M > dsb::kMaxRegMeas) {
+        // chunk-major copy for the many-measurement kernels: (chunk, measurement, step in chunk, xyz)
+        const int64_t C = dsb::kTimeChunk, n_chunks = (T + C - 1) / C;
+        std::vector<double> gc((size_t)(n_chunks * M * C * 3), 0.0);
+        for (int64_t m = 0; m < M; ++m)
+            for (int64_t t = 0; t < T; ++t)
+                memcpy(&gc[(size_t)((((t / C) * M + m) * C + t % C) * 3)], gradient + (m * T + t) * 3, 3 * sizeof(double));
+        DSB_TRY(cudaMalloc(&s->d_grad_chunked, gc.size() * sizeof(double)));
+        DSB_TRY(cudaMemcpy(s->d_grad_chunked, gc.data(), gc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
 #undef DSB_TRY
     if (params->substrate == DSB_MESH) {
         rc = upload_mesh(params->mesh, s->mesh);
@@ -482,6 +493,7 @@ int dsb_run(dsb_sim *s, int64_t t0, int64_t t1)
     memcpy(kp.Rinv, P.R_inv, sizeof kp.Rinv);
     memcpy(kp.ax, P.semiaxes, sizeof kp.ax);
     kp.grad = s->d_grad;
+    kp.grad_chunked = s->d_grad_chunked;
     kp.pos = s->d_pos;
     kp.rng = s->d_rng;
     kp.phases = s->d_phases;

@@ -19,7 +19,11 @@ namespace dsb {
 #endif
 constexpr int kBlock = DSB_BLOCK;    // threads (= walkers) per CTA
 constexpr int kMaxRegMeas = 4;       // measurements whose phase lives in registers
-constexpr int kTimeChunk = 8;        // steps buffered per phase pass when n_meas is larger
+#ifndef DSB_TIMECHUNK
+#define DSB_TIMECHUNK 8
+#endif
+constexpr int kTimeChunk = DSB_TIMECHUNK;  // steps buffered per phase pass when n_meas is larger
+constexpr int kGradRows = 32;              // measurements per gradient tile staged in shared memory
 
 struct MeshDev {
     const double *tri;      // (n_faces, kTriStride): A, B-A, C-A, pad
@@ -46,6 +50,7 @@ struct KParams {
     double step_l, gamma_dt, eps, radius;
     double R[9], Rinv[9], ax[3];
     const double *grad;         // (n_meas, n_t, 3)
+    const double *grad_chunked; // (ceil(n_t / kTimeChunk), n_meas, kTimeChunk, 3), zero padded
     double *pos;                // (n_walkers, 3)
     unsigned long long *rng;    // (n_walkers, 2)
     double *phases;             // (n_meas, n_walkers)
@@ -293,12 +298,15 @@ struct MeshScratch {
     unsigned long long best_d[32];  // closest hit distance per walker (bit pattern of a positive double)
     unsigned best_key[32];          // visiting-order number of the first triangle at that distance
     int best_tri[32];               // that triangle
-    uint4 range_box[kRangeCap];     // segment box for the filter (3 words); owner lane | image flags << 8 | order << 16
+    union {                         // (the hit distances are written after the last use of the boxes)
+        uint4 range_box[kRangeCap];     // segment box for the filter (3 words); owner lane | image flags << 8 | order << 16
+        double hit[kSurvivorCap];       // distance found for the survivor (inf: none)
+    };
     int2 range_pos[kRangeCap];      // number of the range's first entry in the warp's flat numbering; its place in the list
     unsigned start_bits[kEntryCap / 32 + 1];    // bit j: a range starts at flat entry j (+ a word of padding)
     unsigned long long survivor[kSurvivorCap];  // triangle (32) | owner lane (8) | image flags (3) << 8 | order (16) << 16
-    double hit[kSurvivorCap];                   // distance found for the survivor (inf: none)
 };
+static_assert(kSurvivorCap * sizeof(double) <= kRangeCap * sizeof(uint4), "hit[] must fit over range_box[]");
 
 // 15-bit grid coordinate of x on an axis of the base voxel (scale = 32767 / xs[-1]); unclamped
 __device__ __forceinline__ int quantize(double x, double scale) { return __double2int_rd(x * scale); }
@@ -330,6 +338,46 @@ struct CellWalk {
         return (cx * g.nsv1 + cy) * g.nsv2 + cz;
     }
 };
+
+// The reference's loops as they are, for one walker: any number of cells, any list length.
+// Taken by walkers on (or within rounding of) a cell or period boundary, with steps longer than
+// the cooperative search handles, or when its tables are full.  Kept out of line: it is rare,
+// and the hot loop stays small.
+__device__ __noinline__ void mesh_closest_hit_alone(const MeshDev &g, const Vec3 &pos, const Vec3 &s, double ex,
+                                                    double ey, double ez, double &min_d, int &closest)
+{
+    const AxisCells ax = axis_cells(g.xs, g.len_xs, g.vox[0], g.inv_vox[0], g.inv_hx, pos.x, ex);
+    const AxisCells ay = axis_cells(g.ys, g.len_ys, g.vox[1], g.inv_vox[1], g.inv_hy, pos.y, ey);
+    const AxisCells az = axis_cells(g.zs, g.len_zs, g.vox[2], g.inv_vox[2], g.inv_hz, pos.z, ez);
+    for (long long ix = 0; ix < ax.count; ++ix) {
+        int cx;
+        double mx;
+        axis_cell(ax, g.len_xs - 1, ix, cx, mx);
+        const double tx = sub_(pos.x, mx == 0.0 ? 0.0 : mul_(mx, g.top[0]));
+        for (long long iy = 0; iy < ay.count; ++iy) {
+            int cy;
+            double my;
+            axis_cell(ay, g.len_ys - 1, iy, cy, my);
+            const double ty = sub_(pos.y, my == 0.0 ? 0.0 : mul_(my, g.top[1]));
+            for (long long iz = 0; iz < az.count; ++iz) {
+                int cz;
+                double mz;
+                axis_cell(az, g.len_zs - 1, iz, cz, mz);
+                const double tz = sub_(pos.z, mz == 0.0 ? 0.0 : mul_(mz, g.top[2]));
+                const Vec3 tr0 = {tx, ty, tz};
+                const int2 r = __ldg(g.cell_rng + ((long long)cx * g.nsv1 + cy) * g.nsv2 + cz);
+                for (int i = r.x; i < r.y; ++i) {
+                    const int id = __ldg(g.tri_idx + i);
+                    const double d = ray_triangle(load_tri(g.tri, id), tr0, s);
+                    if (d > 0 && d < min_d) {
+                        closest = id;
+                        min_d = d;
+                    }
+                }
+            }
+        }
+    }
+}
 
 // Closest triangle hit (d > 0) over every triangle listed in the cells the segment
 // [pos, pos + step_l * s] overlaps, visited in the reference's order (cells x -> y -> z, entries
@@ -530,37 +578,7 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
             closest = sc.best_tri[lane];
         }
     } else if (need) {  // boundary cases, long segments, table overflow: this lane walks its own cells
-        const AxisCells ax = axis_cells(g.xs, g.len_xs, g.vox[0], g.inv_vox[0], g.inv_hx, pos.x, ex);
-        const AxisCells ay = axis_cells(g.ys, g.len_ys, g.vox[1], g.inv_vox[1], g.inv_hy, pos.y, ey);
-        const AxisCells az = axis_cells(g.zs, g.len_zs, g.vox[2], g.inv_vox[2], g.inv_hz, pos.z, ez);
-        for (long long ix = 0; ix < ax.count; ++ix) {
-            int cx;
-            double mx;
-            axis_cell(ax, g.len_xs - 1, ix, cx, mx);
-            const double tx = sub_(pos.x, mx == 0.0 ? 0.0 : mul_(mx, g.top[0]));
-            for (long long iy = 0; iy < ay.count; ++iy) {
-                int cy;
-                double my;
-                axis_cell(ay, g.len_ys - 1, iy, cy, my);
-                const double ty = sub_(pos.y, my == 0.0 ? 0.0 : mul_(my, g.top[1]));
-                for (long long iz = 0; iz < az.count; ++iz) {
-                    int cz;
-                    double mz;
-                    axis_cell(az, g.len_zs - 1, iz, cz, mz);
-                    const double tz = sub_(pos.z, mz == 0.0 ? 0.0 : mul_(mz, g.top[2]));
-                    const Vec3 tr0 = {tx, ty, tz};
-                    const int2 r = __ldg(g.cell_rng + ((long long)cx * g.nsv1 + cy) * g.nsv2 + cz);
-                    for (int i = r.x; i < r.y; ++i) {
-                        const int id = __ldg(g.tri_idx + i);
-                        const double d = ray_triangle(load_tri(g.tri, id), tr0, s);
-                        if (d > 0 && d < min_d) {
-                            closest = id;
-                            min_d = d;
-                        }
-                    }
-                }
-            }
-        }
+        mesh_closest_hit_alone(g, pos, s, ex, ey, ez, min_d, closest);
     }
 }
 
@@ -577,40 +595,88 @@ __device__ __forceinline__ void mesh_collision(const MeshDev &g, Vec3 &pos, Vec3
         cross_membrane(pos, s, min_d, n, eps);
 }
 
-// simulations.py:878-1013, one whole time step.  Warp-synchronous: every lane of the warp must
-// call it (live == false for lanes without a walker); the collision search of each iteration is
-// shared by the warp.
-__device__ __forceinline__ bool mesh_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab, const bool live)
+// Time steps [t_begin, t_end) of a mesh walk for the 32 walkers of a warp; done(t) is called by
+// a lane when its walker has completed step t (pos = the new position).
+//
+// The collision search is shared by the warp (mesh_closest_hit), so a second search for the one
+// or two walkers that bounced costs about as much as the first one for all 32.  The lanes are
+// therefore not kept in lock step: a walker that bounced stays in flight and takes part in the
+// warp's next search together with the other lanes' next time steps.  Every walker still
+// executes exactly its own sequence of operations (simulations.py:878-1013).
+template <typename Done>
+__device__ __forceinline__ void mesh_walk(const KParams &p, const double *tab, const bool active, const int t_begin,
+                                          const int t_end, Vec3 &pos, Rng &rng, bool &exc, Done done)
 {
     __shared__ MeshScratch s_scratch[kBlock / 32];
     MeshScratch &sc = s_scratch[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const MeshDev &g = p.mesh;
-    __syncwarp();  // lanes leave the previous step's collision loop at different times
-    Vec3 s = random_step(rng, tab);
-    double step_l = p.step_l;
-    int iter = 0;
-    bool check = live;
-    int closest = 0;
+    int t = t_begin, iter = 0, closest = 0;
+    bool in_flight = false;
+    Vec3 s = {0.0, 0.0, 0.0};
+    double step_l = 0.0;
     for (;;) {
-        const bool need = check && step_l > 0 && iter < p.max_iter;
-        if (!__any_sync(0xffffffffu, need)) break;
+        const bool fresh = active && !in_flight && t < t_end;
+        if (!__any_sync(0xffffffffu, fresh || in_flight)) break;
+        if (fresh) {
+            s = random_step(rng, tab);
+            step_l = p.step_l;
+            iter = 0;
+            in_flight = true;
+        }
+        const bool need = in_flight && step_l > 0 && iter < p.max_iter;
         if (need) ++iter;
         double min_d;
         mesh_closest_hit(g, sc, lane, need, pos, s, step_l, min_d, closest);
-        if (need) {
-            if (min_d > step_l) {
-                check = false;
-            } else {
+        if (in_flight) {
+            if (need && !(min_d > step_l)) {
                 mesh_collision(g, pos, s, rng, min_d, closest, p.eps);
                 step_l = sub_(step_l, min_d);
+            } else {
+                pos.x = fma_(step_l, s.x, pos.x);
+                pos.y = fma_(step_l, s.y, pos.y);
+                pos.z = fma_(step_l, s.z, pos.z);
+                exc |= iter >= p.max_iter;
+                done(t);
+                ++t;
+                in_flight = false;
             }
         }
     }
-    pos.x = fma_(step_l, s.x, pos.x);
-    pos.y = fma_(step_l, s.y, pos.y);
-    pos.z = fma_(step_l, s.z, pos.z);
-    return iter >= p.max_iter;
+}
+
+// ---------------------------------------------------------------- TMA bulk copy + mbarrier
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+
+// one thread: announce `bytes` and start the bulk copy global -> shared that will deliver them
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DSB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DSB_DONE_%=;\n"
+        "bra DSB_WAIT_%=;\n"
+        "DSB_DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 // ---------------------------------------------------------------- block reduction of the signal
@@ -656,8 +722,8 @@ __device__ __forceinline__ void block_signal(const KParams &p, bool valid, Phase
 template <int SUB>
 __device__ __forceinline__ bool time_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab, const bool live)
 {
+    static_assert(SUB != 4, "the mesh walk has its own time loop (mesh_walk)");
     if constexpr (SUB == 0) return free_step(pos, rng, p, tab, live);
-    else if constexpr (SUB == 4) return mesh_step(pos, rng, p, tab, live);
     else return walker_step<SUB>(pos, rng, p, tab, live);
 }
 
@@ -670,7 +736,7 @@ constexpr int kParkFlush = DSB_PARK;  // parked walkers per warp that trigger a 
 // are buffered in registers, then each measurement's phase makes one round trip through its
 // (coalesced, L2-resident) row of `phases` per chunk instead of one per step.
 template <int SUB, int MR>
-__global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : DSB_MIN_BLOCKS) walk_kernel(const __grid_constant__ KParams p)
+__global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR == 0 ? 4 : DSB_MIN_BLOCKS)) walk_kernel(const __grid_constant__ KParams p)
 {
     __shared__ double s_tab[16];
     if (threadIdx.x < 16) s_tab[threadIdx.x] = __longlong_as_double((long long)c_sincos_tab[threadIdx.x]);
@@ -740,48 +806,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : DSB_M
                 }
             }
         } else if constexpr (SUB == 4) {
-            // The collision search is shared by the warp (mesh_closest_hit), so a second search
-            // for the one or two walkers that bounced costs about as much as the first one for
-            // all 32.  The lanes are therefore not kept in lock step: a walker that bounced stays
-            // in flight and takes part in the warp's next search together with the other lanes'
-            // next time steps.  Every walker still executes exactly its own sequence of
-            // operations (simulations.py:878-1013).
-            __shared__ MeshScratch s_scratch[kBlock / 32];
-            MeshScratch &sc = s_scratch[threadIdx.x >> 5];
-            const int lane = threadIdx.x & 31;
-            const MeshDev &g = p.mesh;
-            int t = p.t0, iter = 0, closest = 0;
-            bool in_flight = false;
-            Vec3 s = {0.0, 0.0, 0.0};
-            double step_l = 0.0;
-            for (;;) {
-                const bool fresh = active && !in_flight && t < p.t1;
-                if (!__any_sync(0xffffffffu, fresh || in_flight)) break;
-                if (fresh) {
-                    s = random_step(rng, s_tab);
-                    step_l = p.step_l;
-                    iter = 0;
-                    in_flight = true;
-                }
-                const bool need = in_flight && step_l > 0 && iter < p.max_iter;
-                if (need) ++iter;
-                double min_d;
-                mesh_closest_hit(g, sc, lane, need, pos, s, step_l, min_d, closest);
-                if (in_flight) {
-                    if (need && !(min_d > step_l)) {
-                        mesh_collision(g, pos, s, rng, min_d, closest, p.eps);
-                        step_l = sub_(step_l, min_d);
-                    } else {
-                        pos.x = fma_(step_l, s.x, pos.x);
-                        pos.y = fma_(step_l, s.y, pos.y);
-                        pos.z = fma_(step_l, s.z, pos.z);
-                        exc |= iter >= p.max_iter;
-                        accumulate(t);
-                        ++t;
-                        in_flight = false;
-                    }
-                }
-            }
+            mesh_walk(p, s_tab, active, p.t0, p.t1, pos, rng, exc, accumulate);
         } else {
             // the time loop is uniform over the block
             for (int t = p.t0; t < p.t1; ++t) {
@@ -808,28 +833,107 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : DSB_M
     } else {
         if (active && p.t0 == 0)
             for (int m = 0; m < p.n_meas; ++m) p.phases[(long long)m * N + w] = 0.0;
+        // positions of one chunk of steps; indexed by the step loop's counter, so it lives in
+        // (L1-resident) local memory rather than in registers: 192 bytes per walker, touched
+        // twice per step, next to 16 * n_meas bytes of phase traffic per chunk
         Vec3 buf[kTimeChunk];
+        __shared__ __align__(128) double s_grad[2][kGradRows * 3 * kTimeChunk];
+        __shared__ unsigned long long s_bar[2];
+        const double *tile = s_grad[0];
+        int n_tiles = 0;  // tiles consumed so far by this block (buffer = n_tiles & 1, parity = bit 1)
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && p.t0 % kTimeChunk == 0 && p.t1 - p.t0 >= kTimeChunk)  // first tile of the first chunk
+            tma_load_1d(s_grad[0], p.grad_chunked + (long long)(p.t0 / kTimeChunk) * p.n_meas * 3 * kTimeChunk,
+                        min(kGradRows, p.n_meas) * 3 * kTimeChunk * 8, &s_bar[0]);
         for (int t = p.t0; t < p.t1; t += kTimeChunk) {
             const int cnt = min(kTimeChunk, p.t1 - t);
-#pragma unroll
-            for (int k = 0; k < kTimeChunk; ++k)
-                if (k < cnt) {
+            if constexpr (SUB == 4) {
+                mesh_walk(p, s_tab, active, t, t + cnt, pos, rng, exc, [&](int tt) { buf[tt - t] = pos; });
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < cnt; ++k) {
                     exc |= time_step<SUB>(pos, rng, p, s_tab, active);
                     buf[k] = pos;
                 }
-            if (active)
+            }
+            if (cnt == kTimeChunk && t % kTimeChunk == 0) {
+                // Whole chunk.  The gradient samples of (chunk, measurement) are one row of
+                // 3 * kTimeChunk doubles in chunk-major order; tiles of kGradRows rows are streamed
+                // through shared memory by TMA bulk copies (double buffered: the next tile, or the
+                // next chunk's first tile, travels while this one is used), so every walker of
+                // the block reads them as broadcast LDS.  Phases stream through with evict-first
+                // loads/stores, four measurements per pass, requested one pass ahead.  Per
+                // (measurement, walker) the steps are added in ascending order, like the
+                // reference does launch by launch.
+                Vec3 b[kTimeChunk];
+#pragma unroll
+                for (int k = 0; k < kTimeChunk; ++k) b[k] = buf[k];
+                constexpr int kRowLen = 3 * kTimeChunk;
+                const double *gc = p.grad_chunked + (long long)(t / kTimeChunk) * p.n_meas * kRowLen;
+                const bool next_chunk = t + 2 * kTimeChunk <= p.t1;
+                double a[4], a_next[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    a_next[j] = (active && j < p.n_meas) ? __ldcs(p.phases + (long long)j * N + w) : 0.0;
+                for (int m0 = 0; m0 < p.n_meas; m0 += 4) {
+                    if (m0 % kGradRows == 0) {  // next tile
+                        const int bufi = n_tiles & 1;
+                        __syncthreads();  // everybody is done with the other buffer
+                        if (threadIdx.x == 0) {
+                            const int m_next = m0 + kGradRows;
+                            if (m_next < p.n_meas)
+                                tma_load_1d(s_grad[bufi ^ 1], gc + (long long)m_next * kRowLen,
+                                            min(kGradRows, p.n_meas - m_next) * kRowLen * 8, &s_bar[bufi ^ 1]);
+                            else if (next_chunk)
+                                tma_load_1d(s_grad[bufi ^ 1], gc + (long long)p.n_meas * kRowLen,
+                                            min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[bufi ^ 1]);
+                        }
+                        mbar_wait(&s_bar[bufi], (n_tiles >> 1) & 1);
+                        tile = s_grad[bufi];
+                        ++n_tiles;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        a[j] = a_next[j];
+                        a_next[j] = (active && m0 + 4 + j < p.n_meas) ? __ldcs(p.phases + (long long)(m0 + 4 + j) * N + w) : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (m0 + j < p.n_meas) {
+                            const double2 *g2 = reinterpret_cast<const double2 *>(tile + ((m0 + j) % kGradRows) * kRowLen);
+                            double g[kRowLen];
+#pragma unroll
+                            for (int q = 0; q < kRowLen / 2; ++q) {
+                                const double2 v = g2[q];
+                                g[2 * q] = v.x;
+                                g[2 * q + 1] = v.y;
+                            }
+#pragma unroll
+                            for (int k = 0; k < kTimeChunk; ++k)
+                                a[j] = fma_(p.gamma_dt,
+                                            fma_(g[3 * k + 2], b[k].z, fma_(g[3 * k], b[k].x, mul_(g[3 * k + 1], b[k].y))),
+                                            a[j]);
+                            if (active) __stcs(p.phases + (long long)(m0 + j) * N + w, a[j]);
+                        }
+                    }
+                }
+            } else if (active) {  // ragged end of the run, or a launch that does not start on a chunk boundary
                 for (int m = 0; m < p.n_meas; ++m) {
                     double *row = p.phases + (long long)m * N + w;
                     double a = *row;
                     const double *g = p.grad + ((long long)m * p.n_t + t) * 3;
-#pragma unroll
-                    for (int k = 0; k < kTimeChunk; ++k)
-                        if (k < cnt) {
-                            double gx = __ldg(g + 3 * k), gy = __ldg(g + 3 * k + 1), gz = __ldg(g + 3 * k + 2);
-                            a = fma_(p.gamma_dt, fma_(gz, buf[k].z, fma_(gx, buf[k].x, mul_(gy, buf[k].y))), a);
-                        }
+                    for (int k = 0; k < cnt; ++k) {
+                        double gx = __ldg(g + 3 * k), gy = __ldg(g + 3 * k + 1), gz = __ldg(g + 3 * k + 2);
+                        a = fma_(p.gamma_dt, fma_(gz, buf[k].z, fma_(gx, buf[k].x, mul_(gy, buf[k].y))), a);
+                    }
                     *row = a;
                 }
+            }
         }
         if (active) {
             if (exc) p.iter_exc[w] = 1;

@@ -24,6 +24,10 @@ def make(case):
         sub, n_t = substrates.sphere(10e-6), 10000
     elif case == "sphere180":
         sub, n_meas, n_t, n = substrates.sphere(10e-6), 180, 1000, 200_000
+    elif case == "ellipsoid180":
+        sub = substrates.ellipsoid(np.array([10e-6, 5e-6, 2.5e-6]),
+                                   utils.vec2vec_rotmat(np.array([1.0, 0, 0]), np.array([1.0, 1.0, 1.0])))
+        n_meas, n_t, n = 180, 1000, 200_000
     elif case == "sphere8":
         sub, n_meas, n_t = substrates.sphere(10e-6), 8, 1000
     elif case == "cylinder":
@@ -33,8 +37,8 @@ def make(case):
                                    utils.vec2vec_rotmat(np.array([1.0, 0, 0]), np.array([1.0, 1.0, 1.0])))
     elif case == "free":
         sub = substrates.free()
-    elif case in ("mesh", "mesh_small"):
-        k = 8 if case == "mesh" else 2
+    elif case in ("mesh", "mesh_small", "mesh180"):
+        k = 2 if case == "mesh_small" else 8
         v, f, pad, _ = meshgen.tube_lattice(k, k, 5e-6, 12e-6, 40e-6, 64, 12)
         t0 = time.time()
         sub = substrates.mesh(v, f, True, padding=pad, init_pos="uniform", n_sv=np.array([50, 50, 50]),
@@ -42,6 +46,8 @@ def make(case):
         print("  mesh: %d triangles, %d cell entries, built in %.2f s" % (len(f), len(sub.triangle_indices),
                                                                         time.time() - t0))
         n_t, n = 1000, 1_000_000
+        if case == "mesh180":
+            n_meas, n = 180, 200_000
     else:
         raise SystemExit("unknown case " + case)
     n_t = int(os.environ.get("KBENCH_NT", n_t))
