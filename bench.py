@@ -47,6 +47,9 @@ FP64_PER_WALKER_STEP = 120 + 25 + 4 * 1
 # HBM bytes the walk must move per walker per launch: position in/out (48), RNG state in/out
 # (32), phase out (8), iter_exc (1)
 HBM_BYTES_PER_WALKER = 48 + 32 + 8 + 1
+# dram__bytes_read.sum + dram__bytes_write.sum of one walk_kernel<sphere,1> launch over 1e6 walkers
+# (profiles/r01_c_walk_sphere_ncu.md; independent of the number of steps in the launch)
+NCU_DRAM_BYTES_PER_LAUNCH = 41.1e6 + 0.67e6
 
 
 def workload():
@@ -121,6 +124,94 @@ def cpu_baseline(sub, g, dt, seconds_target=15.0, threads=None):
                       "init, %.1f s" % (n, N_T, el)}, n
 
 
+# FP64 instructions per unit of the reference's algorithm (read off its SASS)
+W_STEP, W_PHASE, W_REFL, W_TRI = 120, 4, 75, 50
+W_CHECK = {"sphere": 25, "cylinder": 30, "ellipsoid": 75}
+L2_PEAK_BYTES_PER_CLK = 6300.0  # LTS throughput cap, /opt/skills/guides/B300_MICROARCH.md "L2 cache"
+
+
+def algorithmic_work(sub, g, dt, n_sample=2048, pos=None):
+    """Work of the reference's algorithm per walker-step on this workload, counted by replaying
+    a sample of walkers through the CPU oracle (`n_checks, n_coll, n_tests, n_cells
+    are counted by ... a CPU replay`).  Returns (fp64 instructions, bytes, counters)."""
+    from oracle import oracle as O
+    if pos is None:
+        pos = O.initial_positions(sub, n_sample, SEED)
+    O.work_counters()
+    O.run_walk(sub, g[:1], dt, DIFFUSIVITY, pos[:n_sample], seed=SEED, n_threads=os.cpu_count() or 1)
+    c = O.work_counters()
+    per = {k: v / max(c["steps"], 1) for k, v in c.items() if k != "steps"}
+    fp64 = (W_STEP + W_PHASE * g.shape[0] + W_CHECK.get(sub.type, 0) * per["checks"]
+            + W_REFL * per["collisions"] + W_TRI * per["tri_tests"])
+    nbytes = 72 * per["tri_tests"] + 8 * per["cells"]
+    return fp64, nbytes, per
+
+
+def secondary_workloads(device, fp64_peak, sm_mhz):
+    """Kernel-only throughput of the other BASELINE.json configurations that fit one GPU
+    (cylinder, many-measurement protocols, the periodic mesh): reported next to the headline
+    number, each with the roofline fraction of its algorithmic work."""
+    from disimpy_b200 import gradients, meshgen, simulations, substrates, utils
+    out = []
+    dirs = meshgen.fibonacci_sphere(60)
+    g180, dt180 = gradients.pgse(10e-3, 30e-3, 1000, [1e9] * 60 + [2e9] * 60 + [3e9] * 60,
+                                 np.vstack([dirs, dirs, dirs]))
+    g1k, dt1k = gradients.pgse(10e-3, 30e-3, 1000, [1e9], [[1.0, 0.0, 0.0]])
+    g1e4, dt1e4 = gradients.pgse(10e-3, 30e-3, N_T, [1e9], [[1.0, 0.0, 0.0]])
+    v, f, pad, _ = meshgen.tube_lattice(8, 8, 5e-6, 12e-6, 40e-6, 64, 12)
+    mesh = substrates.mesh(v, f, True, padding=pad, init_pos="extra", n_sv=np.array([50, 50, 50]),
+                           quiet=True)
+    ell = substrates.ellipsoid(np.array([10e-6, 5e-6, 2.5e-6]),
+                               utils.vec2vec_rotmat(np.array([1.0, 0, 0]), np.array([1.0, 1.0, 1.0])))
+    cyl = substrates.cylinder(5e-6, np.array([0.0, 0.0, 1.0]))
+    cases = [
+        ("cylinder r=5um, 1e6 walkers x %d steps, 1 measurement" % N_T, cyl, g1e4, dt1e4, 1_000_000),
+        ("sphere r=10um, 1e6 walkers x 1000 steps, 180 measurements", substrates.sphere(RADIUS), g180, dt180, 1_000_000),
+        ("ellipsoid 10x5x2.5um rotated, 1e6 walkers x 1000 steps, 60 directions x 3 shells", ell, g180, dt180, 1_000_000),
+        ("periodic mesh of 8x8 tubes (98304 triangles, n_sv 50^3), init_pos extra, 1e6 walkers x 1000 steps, 1 measurement", mesh, g1k, dt1k, 1_000_000),
+        ("same mesh, 1e6 walkers x 1000 steps, 180 measurements", mesh, g180, dt180, 1_000_000),
+    ]
+    mesh_pos = None
+    for name, sub, g, dt, n in cases:
+        step_l = np.sqrt(6 * DIFFUSIVITY * dt)
+        np.random.seed(SEED)
+        if sub.type == "sphere":
+            pos = simulations._fill_sphere(n, sub.radius, SEED)
+        elif sub.type == "cylinder":
+            pos = simulations._initial_positions_cylinder(n, sub.radius, np.eye(3), SEED)
+        elif sub.type == "ellipsoid":
+            pos = simulations._initial_positions_ellipsoid(n, sub.semiaxes, sub.R, SEED)
+        else:
+            if mesh_pos is None:
+                mesh_pos = simulations._fill_mesh(n, sub, False, SEED)
+            pos = mesh_pos
+        params, keep = simulations.make_params(sub, n, 0, g, dt, step_l, SEED, 1000, 1e-13, device=device)
+        walk = simulations.Walk(params, g)
+        best = None
+        for _ in range(3):
+            walk.set_positions(pos)
+            walk.run()
+            sig, n_valid = walk.signal()
+            ms, _ = walk.run_stats()
+            best = ms if best is None else min(best, ms)
+        walk.close()
+        rate = n * g.shape[1] / (best * 1e-3)
+        fp64, nbytes, per = algorithmic_work(sub, g, dt, pos=pos)
+        entry = {"workload": name, "value": rate, "unit": UNIT, "kernel_ms": best,
+                 "signal0_over_n": float(sig[0]) / n, "n_valid": int(n_valid),
+                 "algorithmic_fp64_instr_per_walker_step": fp64,
+                 "fp64_frac": fp64 * rate / fp64_peak,
+                 "reference_work_per_walker_step": per}
+        if sub.type == "mesh":
+            l2_peak = L2_PEAK_BYTES_PER_CLK * (sm_mhz or 1965.0) * 1e6
+            entry["algorithmic_bytes_per_walker_step"] = nbytes
+            entry["l2"] = {"achieved_gbs": nbytes * rate / 1e9, "peak_gbs": l2_peak / 1e9,
+                           "frac": nbytes * rate / l2_peak,
+                           "peak_source": "6300 B/clk LTS cap (B300_MICROARCH.md) x SM clock"}
+        out.append(entry)
+    return out
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's algorithm on the host cores (oracle port; the Python
     reference itself only has a GPU path and a ~600 walker-steps/s Numba simulator)."""
@@ -163,6 +254,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
 
@@ -253,6 +345,7 @@ def main():
     # roofline of the dominant kernel (walk_kernel<sphere, 1 measurement>)
     peak = ctypes.c_double(0)
     _lib.check(_lib.lib().dsb_measure_fp64_peak(local_rank, ctypes.byref(peak)), "fp64 peak")
+    fp64_counted, _, per_step = algorithmic_work(sub, g, dt, n_sample=512) if rank == 0 else (FP64_PER_WALKER_STEP, 0, {})
     achieved_fp64 = FP64_PER_WALKER_STEP * (hi - lo) * N_T / (kernel_ms * 1e-3)
     peaks = {}
     try:
@@ -263,9 +356,13 @@ def main():
     hbm_achieved = HBM_BYTES_PER_WALKER * (hi - lo) / (kernel_ms * 1e-3) / 1e9
     roofline = {
         "bound": "fp64", "achieved": achieved_fp64 / 1e12, "peak": peak.value / 1e12,
-        "unit": "T FP64-instr/s", "frac": achieved_fp64 / peak.value, "traffic": None,
+        "unit": "T FP64-instr/s", "frac": achieved_fp64 / peak.value, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
         "kernel": "walk_kernel<sphere,1>", "kernel_ms": kernel_ms,
         "algorithmic_fp64_instr_per_walker_step": FP64_PER_WALKER_STEP,
+        "with_collisions": {"fp64_instr_per_walker_step": fp64_counted,
+                            "frac": fp64_counted * (hi - lo) * N_T / (kernel_ms * 1e-3) / peak.value,
+                            "reference_work_per_walker_step": per_step},
+        "traffic_bytes_per_launch_ncu": NCU_DRAM_BYTES_PER_LAUNCH,
         "peak_source": "measured live by dsb_measure_fp64_peak (independent DFMA chains); "
                        "MEASURED_PEAKS.json has no FP64 figure",
         "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": hbm_peak,
@@ -297,6 +394,9 @@ def main():
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base, _ = cpu_baseline(sub, g, dt)
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        secondary = secondary_workloads(local_rank, peak.value, (clocks or {}).get("sm_mhz"))
 
     if rank == 0:
         line = {
@@ -311,6 +411,7 @@ def main():
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
             "signal": float(signal), "n_valid": int(n_valid),
+            "other_workloads": secondary,
         }
         print(json.dumps(line), flush=True)
     walk.close()

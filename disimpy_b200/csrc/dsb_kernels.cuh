@@ -727,10 +727,20 @@ __device__ __forceinline__ bool time_step(Vec3 &pos, Rng &rng, const KParams &p,
     else return walker_step<SUB>(pos, rng, p, tab, live);
 }
 
+// Parked walkers per warp that trigger a bounce pass (1: collisions are handled inline, step by
+// step).  Measured on a B200 (tools/kbench.py, 1e6 walkers): batching pays when the bounce is
+// expensive (ellipsoid: +9 % at 6), not for the sphere and the cylinder (-3 % at 4), where the
+// lanes idling next to parked walkers cost more than the bounce code saves.
 #ifndef DSB_PARK
-#define DSB_PARK 4
+#define DSB_PARK 1
 #endif
-constexpr int kParkFlush = DSB_PARK;  // parked walkers per warp that trigger a bounce pass
+#ifndef DSB_PARK_ELLIPSOID
+#define DSB_PARK_ELLIPSOID 6
+#endif
+template <int SUB>
+struct ParkFlush {
+    static constexpr int value = SUB == 3 ? DSB_PARK_ELLIPSOID : DSB_PARK;
+};
 
 // MR > 0: n_meas == MR phases in registers.  MR == 0: any n_meas; positions of kTimeChunk steps
 // are buffered in registers, then each measurement's phase makes one round trip through its
@@ -770,12 +780,12 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                 ph[m] = fma_(p.gamma_dt, fma_(gz, pos.z, fma_(gx, pos.x, mul_(gy, pos.y))), ph[m]);
             }
         };
-        if constexpr (SUB >= 1 && SUB <= 3 && kParkFlush > 1) {
+        if constexpr (SUB >= 1 && SUB <= 3 && ParkFlush<SUB>::value > 1) {
             // Collisions are rare per walker and step but not per warp: taken inline, the
             // reflection code would run for one or two lanes in most steps of every warp.  So
             // the lanes of a warp are not kept in lock step: a walker that hits the wall is
             // parked with its step in flight while the other lanes go on with their next steps,
-            // and once kParkFlush walkers of the warp are parked (ballot) they are bounced
+            // and once ParkFlush<SUB>::value walkers of the warp are parked (ballot) they are bounced
             // together.  Every walker still executes exactly its own sequence of operations,
             // so results do not depend on the grouping.
             const unsigned full = 0xffffffffu;
@@ -789,7 +799,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                 const unsigned m_fresh = __ballot_sync(full, fresh);
                 if ((m_parked | m_fresh) == 0) break;
                 bool moved;
-                if (__popc(m_parked) >= kParkFlush || m_fresh == 0) {
+                if (__popc(m_parked) >= ParkFlush<SUB>::value || m_fresh == 0) {
                     moved = parked;
                     if (parked) bounce<SUB>(f, p);
                 } else {

@@ -211,6 +211,19 @@ def run_walk(substrate, gradient, dt, diffusivity, positions, seed=123, max_iter
     return out
 
 
+COUNTER_NAMES = ("checks", "collisions", "tri_tests", "cells", "searches", "steps")
+
+
+def work_counters(reset=True):
+    """What the reference's algorithm did since the last reset, summed over walkers and threads:
+    distance checks (analytic substrates), collisions, ray-triangle tests, grid cells visited,
+    collision searches (mesh) and walker-steps.  bench.py turns them into the algorithmic work
+    per walker-step of its rooflines."""
+    out = np.zeros(len(COUNTER_NAMES), dtype=np.int64)
+    lib().oracle_counters(_ptr(out), ctypes.c_int(1 if reset else 0))
+    return dict(zip(COUNTER_NAMES, (int(v) for v in out)))
+
+
 def signals_from_phases(phases, iter_exc, all_signals=False):
     """disimpy/simulations.py:1413-1421."""
     ph = phases.copy()
