@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -136,6 +137,73 @@ int launch_rng_init(int device, uint64_t seed, uint64_t start, int64_t n, ulongl
     return DSB_OK;
 }
 
+// ------------------------------------------------------------- device buffer cache
+
+// cudaMalloc / cudaFree synchronise the device and cost from a few to tens of milliseconds per
+// simulation() call (more when another allocator holds most of the memory), so buffers of
+// destroyed handles are kept per device and size and handed to the next handle.
+struct BufferCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> idle;
+    std::map<void *, std::pair<int, size_t>> live;
+    size_t idle_bytes = 0;
+    static constexpr size_t kMaxIdleBytes = size_t(16) << 30;
+} g_cache;
+
+cudaError_t cache_malloc(void **out, size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bytes = std::max<size_t>(bytes, 1);
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        auto it = g_cache.idle.find({dev, bytes});
+        if (it != g_cache.idle.end()) {
+            *out = it->second;
+            g_cache.idle.erase(it);
+            g_cache.idle_bytes -= bytes;
+            g_cache.live[*out] = {dev, bytes};
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // give the idle buffers back and retry
+        cudaGetLastError();
+        dsb_release_cache();
+        e = cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        g_cache.live[*out] = {dev, bytes};
+    }
+    return e;
+}
+
+void cache_free(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    auto it = g_cache.live.find(p);
+    if (it == g_cache.live.end()) {
+        cudaFree(p);
+        return;
+    }
+    const std::pair<int, size_t> key = it->second;
+    g_cache.live.erase(it);
+    if (g_cache.idle_bytes + key.second > BufferCache::kMaxIdleBytes) {
+        cudaFree(p);
+        return;
+    }
+    g_cache.idle.insert({key, p});
+    g_cache.idle_bytes += key.second;
+}
+
+template <typename T>
+cudaError_t cache_malloc(T **out, size_t bytes)
+{
+    return cache_malloc(reinterpret_cast<void **>(out), bytes);
+}
+
 // ------------------------------------------------------------- mesh upload
 
 struct MeshBuffers {
@@ -147,13 +215,13 @@ struct MeshBuffers {
     dsb::MeshDev dev{};
     void release()
     {
-        cudaFree(tri);
-        cudaFree(tri_idx);
-        cudaFree(entry);
-        cudaFree(cell_rng);
-        cudaFree(xs);
-        cudaFree(ys);
-        cudaFree(zs);
+        cache_free(tri);
+        cache_free(tri_idx);
+        cache_free(entry);
+        cache_free(cell_rng);
+        cache_free(xs);
+        cache_free(ys);
+        cache_free(zs);
         *this = MeshBuffers();
     }
 };
@@ -220,14 +288,14 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
         if (a < 0 || b < a || b > m.n_triangle_indices) return fail(DSB_EINVAL, "mesh: subvoxel range out of bounds");
         cells[(size_t)c] = make_int2((int)a, (int)b);
     }
-    DSB_CUDA(cudaMalloc(&mb.tri, tri.size() * sizeof(double)));
-    DSB_CUDA(cudaMalloc(&mb.tri_idx, (tri_idx.size() + 1) * sizeof(int)));
-    DSB_CUDA(cudaMalloc(&mb.entry, entry.size() * sizeof(uint4)));
+    DSB_CUDA(cache_malloc(&mb.tri, tri.size() * sizeof(double)));
+    DSB_CUDA(cache_malloc(&mb.tri_idx, (tri_idx.size() + 1) * sizeof(int)));
+    DSB_CUDA(cache_malloc(&mb.entry, entry.size() * sizeof(uint4)));
     DSB_CUDA(cudaMemcpy(mb.entry, entry.data(), entry.size() * sizeof(uint4), cudaMemcpyHostToDevice));
-    DSB_CUDA(cudaMalloc(&mb.cell_rng, cells.size() * sizeof(int2)));
-    DSB_CUDA(cudaMalloc(&mb.xs, (m.n_sv[0] + 1) * sizeof(double)));
-    DSB_CUDA(cudaMalloc(&mb.ys, (m.n_sv[1] + 1) * sizeof(double)));
-    DSB_CUDA(cudaMalloc(&mb.zs, (m.n_sv[2] + 1) * sizeof(double)));
+    DSB_CUDA(cache_malloc(&mb.cell_rng, cells.size() * sizeof(int2)));
+    DSB_CUDA(cache_malloc(&mb.xs, (m.n_sv[0] + 1) * sizeof(double)));
+    DSB_CUDA(cache_malloc(&mb.ys, (m.n_sv[1] + 1) * sizeof(double)));
+    DSB_CUDA(cache_malloc(&mb.zs, (m.n_sv[2] + 1) * sizeof(double)));
     DSB_CUDA(cudaMemcpy(mb.tri, tri.data(), tri.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (!tri_idx.empty())
         DSB_CUDA(cudaMemcpy(mb.tri_idx, tri_idx.data(), tri_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -269,12 +337,16 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
 struct dsb_sim {
     dsb_params prm{};
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // every other part of a part-by-part run (dsb_run_part)
+    cudaEvent_t ev_rewind = nullptr, ev_parts = nullptr;
+    int part_parity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double *d_grad = nullptr, *d_grad_chunked = nullptr, *d_pos = nullptr, *d_phases = nullptr, *d_partials = nullptr, *d_signal = nullptr;
     unsigned long long *d_rng = nullptr, *d_rng0 = nullptr;
     unsigned char *d_exc = nullptr;
     MeshBuffers mesh;
     int64_t t_cur = -1;  // -1: positions not set
+    int64_t parts_done = 0;  // walkers advanced by dsb_run_part since the last rewind
     int grid = 0;
     double kernel_ms = 0.0;
     int64_t n_launches = 0;
@@ -332,6 +404,21 @@ int sync_stats(dsb_sim *s)
 extern "C" {
 
 const char *dsb_last_error(void) { return g_err.c_str(); }
+
+int dsb_release_cache(void)
+{
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (auto &kv : g_cache.idle) {
+        cudaSetDevice(kv.first.first);
+        cudaFree(kv.second);
+    }
+    g_cache.idle.clear();
+    g_cache.idle_bytes = 0;
+    cudaSetDevice(dev);
+    return DSB_OK;
+}
 const char *dsb_version(void) { return "disimpy_b200 0.1 (sm_100a)"; }
 
 int dsb_device_count(int32_t *count)
@@ -349,23 +436,27 @@ int dsb_destroy(dsb_sim *s)
     if (!s) return DSB_OK;
     cudaSetDevice(s->prm.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->stream2) cudaStreamSynchronize(s->stream2);
     for (auto &pr : s->pending) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
     }
     if (s->timer0) cudaEventDestroy(s->timer0);
     if (s->timer1) cudaEventDestroy(s->timer1);
-    cudaFree(s->d_grad);
-    cudaFree(s->d_grad_chunked);
-    cudaFree(s->d_pos);
-    cudaFree(s->d_phases);
-    cudaFree(s->d_partials);
-    cudaFree(s->d_signal);
-    cudaFree(s->d_rng);
-    cudaFree(s->d_rng0);
-    cudaFree(s->d_exc);
+    cache_free(s->d_grad);
+    cache_free(s->d_grad_chunked);
+    cache_free(s->d_pos);
+    cache_free(s->d_phases);
+    cache_free(s->d_partials);
+    cache_free(s->d_signal);
+    cache_free(s->d_rng);
+    cache_free(s->d_rng0);
+    cache_free(s->d_exc);
     s->mesh.release();
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->stream2) cudaStreamDestroy(s->stream2);
+    if (s->ev_rewind) cudaEventDestroy(s->ev_rewind);
+    if (s->ev_parts) cudaEventDestroy(s->ev_parts);
     delete s;
     return DSB_OK;
 }
@@ -397,14 +488,17 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
         }                             \
     } while (0)
     DSB_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    DSB_TRY(cudaMalloc(&s->d_grad, sizeof(double) * 3 * M * T));
-    DSB_TRY(cudaMalloc(&s->d_pos, sizeof(double) * 3 * N));
-    DSB_TRY(cudaMalloc(&s->d_phases, sizeof(double) * M * N));
-    DSB_TRY(cudaMalloc(&s->d_partials, sizeof(double) * (M + 1) * s->grid));
-    DSB_TRY(cudaMalloc(&s->d_signal, sizeof(double) * (M + 1)));
-    DSB_TRY(cudaMalloc(&s->d_rng, sizeof(unsigned long long) * 2 * N));
-    DSB_TRY(cudaMalloc(&s->d_rng0, sizeof(unsigned long long) * 2 * N));
-    DSB_TRY(cudaMalloc(&s->d_exc, N));
+    DSB_TRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    DSB_TRY(cudaEventCreateWithFlags(&s->ev_rewind, cudaEventDisableTiming));
+    DSB_TRY(cudaEventCreateWithFlags(&s->ev_parts, cudaEventDisableTiming));
+    DSB_TRY(cache_malloc(&s->d_grad, sizeof(double) * 3 * M * T));
+    DSB_TRY(cache_malloc(&s->d_pos, sizeof(double) * 3 * N));
+    DSB_TRY(cache_malloc(&s->d_phases, sizeof(double) * M * N));
+    DSB_TRY(cache_malloc(&s->d_partials, sizeof(double) * (M + 1) * s->grid));
+    DSB_TRY(cache_malloc(&s->d_signal, sizeof(double) * (M + 1)));
+    DSB_TRY(cache_malloc(&s->d_rng, sizeof(unsigned long long) * 2 * N));
+    DSB_TRY(cache_malloc(&s->d_rng0, sizeof(unsigned long long) * 2 * N));
+    DSB_TRY(cache_malloc(&s->d_exc, N));
     DSB_TRY(cudaMemcpyAsync(s->d_grad, gradient, sizeof(double) * 3 * M * T, cudaMemcpyHostToDevice, s->stream));
     if (M > dsb::kMaxRegMeas) {
         // chunk-major copy for the many-measurement kernels: (chunk, measurement, step in chunk, xyz)
@@ -413,7 +507,7 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
         for (int64_t m = 0; m < M; ++m)
             for (int64_t t = 0; t < T; ++t)
                 memcpy(&gc[(size_t)((((t / C) * M + m) * C + t % C) * 3)], gradient + (m * T + t) * 3, 3 * sizeof(double));
-        DSB_TRY(cudaMalloc(&s->d_grad_chunked, gc.size() * sizeof(double)));
+        DSB_TRY(cache_malloc(&s->d_grad_chunked, gc.size() * sizeof(double)));
         DSB_TRY(cudaMemcpy(s->d_grad_chunked, gc.data(), gc.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
 #undef DSB_TRY
@@ -447,7 +541,10 @@ static int rewind_sim(dsb_sim *s)
         cudaEventDestroy(pr.second);
     }
     s->pending.clear();
+    DSB_CUDA(cudaEventRecord(s->ev_rewind, s->stream));
     s->t_cur = 0;
+    s->parts_done = 0;
+    s->part_parity = 0;
     s->kernel_ms = 0.0;
     s->n_launches = 0;
     s->finalized = false;
@@ -470,15 +567,15 @@ int dsb_set_positions_dev(dsb_sim *s, const double *positions_dev)
     return rewind_sim(s);
 }
 
-int dsb_run(dsb_sim *s, int64_t t0, int64_t t1)
+// one launch of the walk kernel: walkers [w0, w1) over time steps [t0, t1)
+static int launch_walk_range(dsb_sim *s, cudaStream_t st, int64_t w0, int64_t w1, int64_t t0, int64_t t1)
 {
-    if (!s) return fail(DSB_EINVAL, "null handle");
-    if (s->t_cur < 0) return fail(DSB_ESTATE, "dsb_run before dsb_set_positions");
-    if (t0 != s->t_cur || t1 <= t0 || t1 > s->prm.n_t) return fail(DSB_EINVAL, "bad step range");
-    DSB_CUDA(cudaSetDevice(s->prm.device));
     const dsb_params &P = s->prm;
     dsb::KParams kp{};
     kp.n_walkers = P.n_walkers;
+    kp.w_begin = w0;
+    kp.w_end = w1;
+    kp.n_blocks_total = s->grid;
     kp.n_meas = (int)P.n_meas;
     kp.n_t = (int)P.n_t;
     kp.t0 = (int)t0;
@@ -500,28 +597,105 @@ int dsb_run(dsb_sim *s, int64_t t0, int64_t t1)
     kp.iter_exc = s->d_exc;
     kp.partials = s->d_partials;
     kp.mesh = s->mesh.dev;
+    const int grid = (int)((w1 - w0 + dsb::kBlock - 1) / dsb::kBlock);
+    cudaEvent_t e0, e1;
+    DSB_CUDA(cudaEventCreate(&e0));
+    DSB_CUDA(cudaEventCreate(&e1));
+    DSB_CUDA(cudaEventRecord(e0, st));
+    switch (P.substrate) {
+    case DSB_FREE: launch_walk<0>(kp, grid, st); break;
+    case DSB_SPHERE: launch_walk<1>(kp, grid, st); break;
+    case DSB_CYLINDER: launch_walk<2>(kp, grid, st); break;
+    case DSB_ELLIPSOID: launch_walk<3>(kp, grid, st); break;
+    default: launch_walk<4>(kp, grid, st); break;
+    }
+    DSB_CUDA(cudaGetLastError());
+    s->n_launches += 1;
+    DSB_CUDA(cudaEventRecord(e1, st));
+    s->pending.emplace_back(e0, e1);
+    return DSB_OK;
+}
+
+static int launch_signal_reduction(dsb_sim *s)
+{
     cudaEvent_t e0, e1;
     DSB_CUDA(cudaEventCreate(&e0));
     DSB_CUDA(cudaEventCreate(&e1));
     DSB_CUDA(cudaEventRecord(e0, s->stream));
-    switch (P.substrate) {
-    case DSB_FREE: launch_walk<0>(kp, s->grid, s->stream); break;
-    case DSB_SPHERE: launch_walk<1>(kp, s->grid, s->stream); break;
-    case DSB_CYLINDER: launch_walk<2>(kp, s->grid, s->stream); break;
-    case DSB_ELLIPSOID: launch_walk<3>(kp, s->grid, s->stream); break;
-    default: launch_walk<4>(kp, s->grid, s->stream); break;
-    }
+    dsb::reduce_partials_kernel<<<(unsigned)(s->prm.n_meas + 1), 256, 0, s->stream>>>(s->d_partials, s->grid, s->d_signal);
     DSB_CUDA(cudaGetLastError());
-    s->n_launches += 1;
-    if (kp.finalize) {
-        dsb::reduce_partials_kernel<<<(unsigned)(P.n_meas + 1), 256, 0, s->stream>>>(s->d_partials, s->grid, s->d_signal);
-        DSB_CUDA(cudaGetLastError());
-        s->n_launches += 1;
-        s->finalized = true;
-    }
     DSB_CUDA(cudaEventRecord(e1, s->stream));
     s->pending.emplace_back(e0, e1);
+    s->n_launches += 1;
+    s->finalized = true;
+    return DSB_OK;
+}
+
+int dsb_run(dsb_sim *s, int64_t t0, int64_t t1)
+{
+    if (!s) return fail(DSB_EINVAL, "null handle");
+    if (s->t_cur < 0) return fail(DSB_ESTATE, "dsb_run before dsb_set_positions");
+    if (s->parts_done > 0) return fail(DSB_ESTATE, "dsb_run after dsb_run_part: finish the run part by part");
+    if (t0 != s->t_cur || t1 <= t0 || t1 > s->prm.n_t) return fail(DSB_EINVAL, "bad step range");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    int rc = launch_walk_range(s, s->stream, 0, s->prm.n_walkers, t0, t1);
+    if (rc) return rc;
+    if (t1 == s->prm.n_t) {
+        rc = launch_signal_reduction(s);
+        if (rc) return rc;
+    }
     s->t_cur = t1;
+    return DSB_OK;
+}
+
+int dsb_rewind(dsb_sim *s)
+{
+    if (!s) return fail(DSB_EINVAL, "null handle");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    return rewind_sim(s);
+}
+
+int dsb_set_positions_part(dsb_sim *s, int64_t w0, int64_t w1, const double *positions)
+{
+    if (!s || !positions) return fail(DSB_EINVAL, "null argument");
+    if (w0 < 0 || w1 <= w0 || w1 > s->prm.n_walkers) return fail(DSB_EINVAL, "bad walker range");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    // consecutive parts alternate between two streams, so that the next part's blocks fill the
+    // SMs while the previous part drains
+    cudaStream_t st = s->part_parity ? s->stream2 : s->stream;
+    if (s->part_parity) DSB_CUDA(cudaStreamWaitEvent(st, s->ev_rewind, 0));
+    DSB_CUDA(cudaMemcpyAsync(s->d_pos + 3 * w0, positions, sizeof(double) * 3 * (w1 - w0), cudaMemcpyHostToDevice, st));
+    return DSB_OK;
+}
+
+int dsb_run_part(dsb_sim *s, int64_t w0, int64_t w1)
+{
+    if (!s) return fail(DSB_EINVAL, "null handle");
+    if (s->t_cur != 0) return fail(DSB_ESTATE, "dsb_run_part needs a rewound handle (dsb_rewind)");
+    if (w0 < 0 || w1 <= w0 || w1 > s->prm.n_walkers || w0 % dsb::kBlock != 0)
+        return fail(DSB_EINVAL, "bad walker range (w0 must be a multiple of 128)");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    cudaStream_t st = s->part_parity ? s->stream2 : s->stream;
+    if (s->part_parity) DSB_CUDA(cudaStreamWaitEvent(st, s->ev_rewind, 0));
+    int rc = launch_walk_range(s, st, w0, w1, 0, s->prm.n_t);
+    if (rc) return rc;
+    s->part_parity ^= 1;
+    s->parts_done += w1 - w0;
+    return DSB_OK;
+}
+
+int dsb_finish(dsb_sim *s)
+{
+    if (!s) return fail(DSB_EINVAL, "null handle");
+    if (s->t_cur != 0 || s->parts_done != s->prm.n_walkers)
+        return fail(DSB_ESTATE, "dsb_finish: the parts run so far do not cover every walker exactly once");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    DSB_CUDA(cudaEventRecord(s->ev_parts, s->stream2));
+    DSB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_parts, 0));
+    int rc = launch_signal_reduction(s);
+    if (rc) return rc;
+    s->t_cur = s->prm.n_t;
+    s->parts_done = 0;
     return DSB_OK;
 }
 
@@ -530,6 +704,7 @@ int dsb_sync(dsb_sim *s)
     if (!s) return fail(DSB_EINVAL, "null handle");
     DSB_CUDA(cudaSetDevice(s->prm.device));
     DSB_CUDA(cudaStreamSynchronize(s->stream));
+    DSB_CUDA(cudaStreamSynchronize(s->stream2));
     return DSB_OK;
 }
 

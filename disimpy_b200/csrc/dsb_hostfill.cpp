@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <new>
 
 namespace {
 
@@ -53,6 +54,61 @@ struct MT19937 {
 
 }  // namespace
 
+struct dsb_host_sampler {
+    MT19937 rng;
+    int shape;
+    double scale[3];
+    dsb_host_sampler(uint32_t seed, int shape_, const double *sc) : rng(seed), shape(shape_)
+    {
+        scale[0] = sc[0];
+        scale[1] = shape_ == 2 ? sc[1] : 0.0;
+        scale[2] = shape_ == 2 ? sc[2] : 0.0;
+    }
+    void next(int64_t n, double *out)
+    {
+        int64_t have = 0;
+        if (shape == 0) {
+            const double r = scale[0];
+            while (have < n) {
+                double x = (rng.next_double() - 0.5) * 2 * r;
+                double y = (rng.next_double() - 0.5) * 2 * r;
+                if (std::sqrt(x * x + y * y) < r) {
+                    out[2 * have] = x;
+                    out[2 * have + 1] = y;
+                    ++have;
+                }
+            }
+        } else if (shape == 1) {
+            const double r = scale[0];
+            while (have < n) {
+                double x = (rng.next_double() - 0.5) * 2 * r;
+                double y = (rng.next_double() - 0.5) * 2 * r;
+                double z = (rng.next_double() - 0.5) * 2 * r;
+                if (std::sqrt(x * x + y * y + z * z) < r) {
+                    out[3 * have] = x;
+                    out[3 * have + 1] = y;
+                    out[3 * have + 2] = z;
+                    ++have;
+                }
+            }
+        } else {
+            const double a = scale[0], b = scale[1], c = scale[2];
+            while (have < n) {
+                double x = (rng.next_double() - 0.5) * 2 * a;
+                double y = (rng.next_double() - 0.5) * 2 * b;
+                double z = (rng.next_double() - 0.5) * 2 * c;
+                double qx = x / a, qy = y / b, qz = z / c;
+                if (qx * qx + qy * qy + qz * qz < 1) {
+                    out[3 * have] = x;
+                    out[3 * have + 1] = y;
+                    out[3 * have + 2] = z;
+                    ++have;
+                }
+            }
+        }
+    }
+};
+
 extern "C" {
 
 // shape: 0 = disc (out is (n,2), scale[0] = radius), 1 = ball (out (n,3), scale[0] = radius),
@@ -60,47 +116,28 @@ extern "C" {
 int dsb_host_fill(int32_t shape, int64_t n, uint64_t seed, const double *scale, double *out)
 {
     if (n < 0 || !scale || (n > 0 && !out) || shape < 0 || shape > 2 || seed > 0xffffffffULL) return DSB_EINVAL;
-    MT19937 rng((uint32_t)seed);
-    int64_t have = 0;
-    if (shape == 0) {
-        const double r = scale[0];
-        while (have < n) {
-            double x = (rng.next_double() - 0.5) * 2 * r;
-            double y = (rng.next_double() - 0.5) * 2 * r;
-            if (std::sqrt(x * x + y * y) < r) {
-                out[2 * have] = x;
-                out[2 * have + 1] = y;
-                ++have;
-            }
-        }
-    } else if (shape == 1) {
-        const double r = scale[0];
-        while (have < n) {
-            double x = (rng.next_double() - 0.5) * 2 * r;
-            double y = (rng.next_double() - 0.5) * 2 * r;
-            double z = (rng.next_double() - 0.5) * 2 * r;
-            if (std::sqrt(x * x + y * y + z * z) < r) {
-                out[3 * have] = x;
-                out[3 * have + 1] = y;
-                out[3 * have + 2] = z;
-                ++have;
-            }
-        }
-    } else {
-        const double a = scale[0], b = scale[1], c = scale[2];
-        while (have < n) {
-            double x = (rng.next_double() - 0.5) * 2 * a;
-            double y = (rng.next_double() - 0.5) * 2 * b;
-            double z = (rng.next_double() - 0.5) * 2 * c;
-            double qx = x / a, qy = y / b, qz = z / c;
-            if (qx * qx + qy * qy + qz * qz < 1) {
-                out[3 * have] = x;
-                out[3 * have + 1] = y;
-                out[3 * have + 2] = z;
-                ++have;
-            }
-        }
-    }
+    dsb_host_sampler s((uint32_t)seed, shape, scale);
+    s.next(n, out);
+    return DSB_OK;
+}
+
+int dsb_host_sampler_create(int32_t shape, uint64_t seed, const double *scale, dsb_host_sampler **out)
+{
+    if (!out || !scale || shape < 0 || shape > 2 || seed > 0xffffffffULL) return DSB_EINVAL;
+    *out = new (std::nothrow) dsb_host_sampler((uint32_t)seed, shape, scale);
+    return *out ? DSB_OK : DSB_ENOMEM;
+}
+
+int dsb_host_sampler_next(dsb_host_sampler *sampler, int64_t n, double *out)
+{
+    if (!sampler || n < 0 || (n > 0 && !out)) return DSB_EINVAL;
+    sampler->next(n, out);
+    return DSB_OK;
+}
+
+int dsb_host_sampler_destroy(dsb_host_sampler *sampler)
+{
+    delete sampler;
     return DSB_OK;
 }
 

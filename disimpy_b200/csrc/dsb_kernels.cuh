@@ -42,7 +42,9 @@ struct MeshDev {
 };
 
 struct KParams {
-    long long n_walkers;
+    long long n_walkers;        // walkers of the handle (row length of `phases`)
+    long long w_begin, w_end;   // walkers this launch advances; w_begin is a multiple of kBlock
+    int n_blocks_total;         // blocks covering all n_walkers (row length of `partials`)
     int n_meas, n_t;
     int t0, t1;
     int finalize;  // t1 == n_t: also emit per-block sum(cos phase) partials
@@ -55,7 +57,7 @@ struct KParams {
     unsigned long long *rng;    // (n_walkers, 2)
     double *phases;             // (n_meas, n_walkers)
     unsigned char *iter_exc;    // (n_walkers,)
-    double *partials;           // (n_meas + 1, gridDim.x)
+    double *partials;           // (n_meas + 1, n_blocks_total)
     MeshDev mesh;
 };
 
@@ -689,7 +691,7 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // phase(m) -> per-block sum of cos(phase) over walkers with a clear iter_exc flag, written to
-// partials[m * gridDim.x + blockIdx.x]; row n_meas receives the number of such walkers.
+// partials[m * n_blocks_total + block]; row n_meas receives the number of such walkers.
 // Fixed summation tree: results do not depend on scheduling.
 template <typename PhaseFn>
 __device__ __forceinline__ void block_signal(const KParams &p, bool valid, PhaseFn phase_of)
@@ -711,7 +713,7 @@ __device__ __forceinline__ void block_signal(const KParams &p, bool valid, Phase
             double acc = 0.0;
 #pragma unroll
             for (int w = 0; w < kBlock / 32; ++w) acc += s_part[w][lane];
-            p.partials[(long long)(m0 + lane) * gridDim.x + blockIdx.x] = acc;
+            p.partials[(long long)(m0 + lane) * p.n_blocks_total + (int)(p.w_begin / kBlock) + blockIdx.x] = acc;
         }
         __syncthreads();
     }
@@ -752,8 +754,8 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
     if (threadIdx.x < 16) s_tab[threadIdx.x] = __longlong_as_double((long long)c_sincos_tab[threadIdx.x]);
     __syncthreads();
 
-    const long long w = (long long)blockIdx.x * kBlock + threadIdx.x;
-    const bool active = w < p.n_walkers;
+    const long long w = p.w_begin + (long long)blockIdx.x * kBlock + threadIdx.x;
+    const bool active = w < p.w_end;
     const long long N = p.n_walkers;
     Vec3 pos = {0.0, 0.0, 0.0};
     Rng rng = {1ull, 1ull};

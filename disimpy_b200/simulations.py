@@ -38,6 +38,40 @@ def _host_fill(shape, n, seed, scale, dim):
     return out
 
 
+class _HostSampler:
+    """The same MT19937 rejection stream as _host_fill, handed out in consecutive stretches, so
+    that simulation() can start the walk of the first walkers while the positions of the next
+    ones are still being drawn (the stream is sequential; the GPU would otherwise idle)."""
+
+    def __init__(self, shape, seed, scale, dim):
+        self._h = ctypes.c_void_p()
+        self._dim = dim
+        sc = _lib.f64(np.atleast_1d(scale))
+        if _lib.lib().dsb_host_sampler_create(shape, seed, _lib.ptr(sc), ctypes.byref(self._h)) != 0:
+            raise ValueError("Seed must be between 0 and 2**32 - 1")
+
+    def next(self, n):
+        out = np.zeros((n, self._dim))
+        _lib.check(_lib.lib().dsb_host_sampler_next(self._h, n, _lib.ptr(out)), "dsb_host_sampler_next")
+        return out
+
+    def skip(self, n, block=1 << 20):
+        while n > 0:
+            self.next(min(n, block))
+            n -= block
+
+    def close(self):
+        if self._h:
+            _lib.lib().dsb_host_sampler_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _fill_circle(n, radius, seed):
     """n points uniform in a disc (simulations.py:353-366) from the MT19937 stream of ``seed``."""
     return _host_fill(0, n, seed, radius, 2)
@@ -202,6 +236,19 @@ class Walk:
     def run(self, t0=0, t1=None):
         _lib.check(self._L.dsb_run(self._h, t0, self.n_t if t1 is None else t1), "dsb_run")
 
+    def rewind(self):
+        _lib.check(self._L.dsb_rewind(self._h), "dsb_rewind")
+
+    def set_positions_part(self, w0, w1, positions):
+        pos = _lib.f64(positions)
+        _lib.check(self._L.dsb_set_positions_part(self._h, w0, w1, _lib.ptr(pos)), "dsb_set_positions_part")
+
+    def run_part(self, w0, w1):
+        _lib.check(self._L.dsb_run_part(self._h, w0, w1), "dsb_run_part")
+
+    def finish(self):
+        _lib.check(self._L.dsb_finish(self._h), "dsb_finish")
+
     def sync(self):
         _lib.check(self._L.dsb_sync(self._h), "dsb_sync")
 
@@ -337,7 +384,14 @@ def simulation(
         print("Step length = %s m" % step_l)
         print("Step duration = %s s" % dt)
 
-    if substrate.type == "free":
+    # Analytic substrates draw their initial positions from one sequential host stream.  When
+    # nothing needs all of them up front (no trajectory file, no progress display) they are
+    # drawn part by part while the GPU already walks the earlier parts.
+    pipelined = substrate.type in ("sphere", "cylinder", "ellipsoid") and not traj and quiet
+    positions = None
+    if pipelined:
+        pass
+    elif substrate.type == "free":
         positions = np.zeros((n_walkers, 3))
     elif substrate.type == "cylinder":
         R = utils.vec2vec_rotmat(substrate.orientation, np.array([1.0, 0, 0]))
@@ -372,8 +426,13 @@ def simulation(
                                epsilon)
     walk = Walk(params, gradient)
     try:
-        walk.set_positions(positions[lo:hi])
-        if traj:
+        if pipelined:
+            _walk_pipelined(walk, substrate, lo, hi, seed)
+        else:
+            walk.set_positions(positions[lo:hi])
+        if pipelined:
+            pass
+        elif traj:
             for t in range(n_t):
                 walk.run(t, t + 1)
                 step_pos = _gather_rows(walk.positions(), n_walkers, lo, hi, dist)
@@ -428,6 +487,49 @@ def simulation(
         return signals
     finally:
         walk.close()
+
+
+_PART = 131072  # walkers per part: about one full wave of 128-walker blocks on a B200
+
+
+def _position_parts(substrate, lo, hi, seed, part=_PART):
+    """Initial positions of global walkers [lo, hi) of an analytic substrate, part by part:
+    yields (a, b, positions of local walkers [a, b)).  Concatenated, the parts are what
+    _fill_sphere / _initial_positions_cylinder / _initial_positions_ellipsoid return in one go
+    (simulations.py:346-418)."""
+    if substrate.type == "sphere":
+        sampler, to_lab = _HostSampler(1, seed, substrate.radius, 3), None
+    elif substrate.type == "cylinder":
+        R = utils.vec2vec_rotmat(substrate.orientation, np.array([1.0, 0, 0]))
+        sampler, to_lab = _HostSampler(0, seed, substrate.radius, 2), np.linalg.inv(R)
+    else:
+        sampler, to_lab = _HostSampler(2, seed, substrate.semiaxes, 3), substrate.R
+    try:
+        sampler.skip(lo)
+        n = hi - lo
+        for a in range(0, n, part):
+            b = min(a + part, n)
+            pts = sampler.next(b - a)
+            if substrate.type == "cylinder":
+                body = np.zeros((b - a, 3))
+                body[:, 1:3] = pts
+                pts = body
+            if to_lab is not None:
+                pts = np.matmul(to_lab, pts.T).T
+            yield a, b, pts
+    finally:
+        sampler.close()
+
+
+def _walk_pipelined(walk, substrate, lo, hi, seed):
+    """Walks every part over all time steps as soon as its positions are there: the host draws
+    the next part while the GPU works.  Same positions, same walk, same signal as drawing
+    everything first."""
+    walk.rewind()
+    for a, b, pts in _position_parts(substrate, lo, hi, seed):
+        walk.set_positions_part(a, b, pts)
+        walk.run_part(a, b)
+    walk.finish()
 
 
 def _allreduce_sum(values, dist):

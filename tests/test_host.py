@@ -323,3 +323,27 @@ def test_two_rank_gloo_sharding(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+def test_position_parts_equal_one_shot_sampling():
+    """simulation() draws the initial positions of analytic substrates part by part (to overlap
+    the sequential host stream with the GPU); the parts must be the one-shot arrays, bit for bit,
+    also for shards that start in the middle of the stream."""
+    from disimpy_b200 import simulations, substrates, utils
+    n = 300_000
+    R = utils.vec2vec_rotmat(np.array([1.0, 0, 0]), np.array([0.3, 1.0, -0.4]))
+    subs = [substrates.sphere(3e-6), substrates.cylinder(2e-6, np.array([0.2, -1.0, 0.5])),
+            substrates.ellipsoid(np.array([3e-6, 2e-6, 1e-6]), R)]
+    for sub in subs:
+        if sub.type == "sphere":
+            full = simulations._fill_sphere(n, sub.radius, 9)
+        elif sub.type == "cylinder":
+            Rc = utils.vec2vec_rotmat(sub.orientation, np.array([1.0, 0, 0]))
+            full = simulations._initial_positions_cylinder(n, sub.radius, np.linalg.inv(Rc), 9)
+        else:
+            full = simulations._initial_positions_ellipsoid(n, sub.semiaxes, sub.R, 9)
+        for lo, hi in ((0, n), (123_457, n)):
+            parts = list(simulations._position_parts(sub, lo, hi, 9, part=65_536))
+            assert [a for a, _, _ in parts] == list(range(0, hi - lo, 65_536))
+            got = np.vstack([pts for _, _, pts in parts])
+            assert np.array_equal(got, full[lo:hi]), sub.type

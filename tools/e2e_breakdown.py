@@ -3,6 +3,9 @@ import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if os.environ.get('WITH_TORCH'):
+    import torch
+    torch.cuda.init(); _x = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
 from disimpy_b200 import gradients, simulations, substrates
 
 n, n_t = 1_000_000, int(os.environ.get("NT", 10000))
