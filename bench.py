@@ -266,6 +266,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # Exactly one JSON line may reach stdout: libraries that print there (NCCL's version banner,
+    # build tools) are sent to stderr, the result goes to the saved descriptor.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import __graft_entry__ as entry
@@ -413,7 +419,8 @@ def main():
             "signal": float(signal), "n_valid": int(n_valid),
             "other_workloads": secondary,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     walk.close()
     if world > 1:
         dist.destroy_process_group()

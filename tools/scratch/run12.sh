@@ -1,0 +1,2 @@
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_r01_2gpu.json 2> gpurun_out/bench_r01_2gpu.err
+tail -c 1500 gpurun_out/bench_r01_2gpu.err; cat gpurun_out/bench_r01_2gpu.json | cut -c1-1200
