@@ -314,7 +314,10 @@ static_assert(kSurvivorCap * sizeof(double) <= kRangeCap * sizeof(uint4), "hit[]
 __device__ __forceinline__ int quantize(double x, double scale) { return __double2int_rd(x * scale); }
 __device__ __forceinline__ unsigned clamp15(int q) { return (unsigned)min(max(q, 0), 32767); }
 
-constexpr int kMaxCells = 12;  // cells per walker and search the cooperative path takes
+#ifndef DSB_MAXCELLS
+#define DSB_MAXCELLS 12
+#endif
+constexpr int kMaxCells = DSB_MAXCELLS;  // cells per walker and search the cooperative path takes
 
 // c-th cell (visiting order x -> y -> z) of the spans: place of its list range, image flags
 struct CellWalk {
@@ -419,13 +422,17 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         n_cells = sx.count * sy.count * sz.count;
         fast = fast && n_cells <= kMaxCells;
     }
-    // list ranges of this lane's cells: independent loads, all in flight together
+    // list ranges of this lane's cells: independent loads, all in flight together; the loops
+    // stop at the largest cell count of the warp
+    const int n_cells_warp = __reduce_max_sync(full, fast ? n_cells : 0);
     int2 rng[kMaxCells];
+#pragma unroll
+    for (int c = 0; c < kMaxCells; ++c) rng[c] = make_int2(0, 0);
     {
         CellWalk cw;
 #pragma unroll
         for (int c = 0; c < kMaxCells; ++c) {
-            rng[c] = make_int2(0, 0);
+            if (c >= n_cells_warp) break;
             if (fast && c < n_cells) {
                 int flags;
                 rng[c] = __ldg(g.cell_rng + cw.index(g, sx, sy, sz, flags));
@@ -478,6 +485,7 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         CellWalk cw;
 #pragma unroll
         for (int c = 0; c < kMaxCells; ++c) {
+            if (c >= n_cells_warp) break;
             const int n = rng[c].y - rng[c].x;
             if (n > 0) {
                 int flags;
