@@ -897,10 +897,10 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                 const double *gc = p.grad_chunked + (long long)(t / kTimeChunk) * p.n_meas * kRowLen;
                 const bool next_chunk = t + 2 * kTimeChunk <= p.t1;
                 double a[4], a_next[4];
+                double *row = p.phases + (active ? w : 0);  // this walker's entry in row m0 (inactive lanes never touch it)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    a_next[j] = (active && j < p.n_meas) ? __ldcs(p.phases + (long long)j * N + w) : 0.0;
-                for (int m0 = 0; m0 < p.n_meas; m0 += 4) {
+                for (int j = 0; j < 4; ++j) a_next[j] = (active && j < p.n_meas) ? __ldcs(row + j * N) : 0.0;
+                for (int m0 = 0; m0 < p.n_meas; m0 += 4, row += 4 * N) {
                     if (m0 % kGradRows == 0) {  // next tile
                         const int bufi = n_tiles & 1;
                         __syncthreads();  // everybody is done with the other buffer
@@ -917,19 +917,20 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                         tile = s_grad[bufi];
                         ++n_tiles;
                     }
+                    const int left = p.n_meas - m0;  // rows from m0 on
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         a[j] = a_next[j];
-                        a_next[j] = (active && m0 + 4 + j < p.n_meas) ? __ldcs(p.phases + (long long)(m0 + 4 + j) * N + w) : 0.0;
+                        a_next[j] = (active && 4 + j < left) ? __ldcs(row + (4 + j) * N) : 0.0;
                     }
+                    const double2 *g2 = reinterpret_cast<const double2 *>(tile + (m0 % kGradRows) * kRowLen);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        if (m0 + j < p.n_meas) {
-                            const double2 *g2 = reinterpret_cast<const double2 *>(tile + ((m0 + j) % kGradRows) * kRowLen);
+                        if (j < left) {
                             double g[kRowLen];
 #pragma unroll
                             for (int q = 0; q < kRowLen / 2; ++q) {
-                                const double2 v = g2[q];
+                                const double2 v = g2[j * (kRowLen / 2) + q];
                                 g[2 * q] = v.x;
                                 g[2 * q + 1] = v.y;
                             }
@@ -938,7 +939,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                                 a[j] = fma_(p.gamma_dt,
                                             fma_(g[3 * k + 2], b[k].z, fma_(g[3 * k], b[k].x, mul_(g[3 * k + 1], b[k].y))),
                                             a[j]);
-                            if (active) __stcs(p.phases + (long long)(m0 + j) * N + w, a[j]);
+                            if (active) __stcs(row + j * N, a[j]);
                         }
                     }
                 }
