@@ -37,12 +37,16 @@ def make(case):
                                    utils.vec2vec_rotmat(np.array([1.0, 0, 0]), np.array([1.0, 1.0, 1.0])))
     elif case == "free":
         sub = substrates.free()
-    elif case in ("mesh", "mesh_small", "mesh180"):
+    elif case in ("mesh", "mesh_small", "mesh180", "mesh_big"):
         k = 2 if case == "mesh_small" else 8
-        v, f, pad, _ = meshgen.tube_lattice(k, k, 5e-6, 12e-6, 40e-6, 64, 12)
+        if case == "mesh_big":  # BASELINE config 5's mesh: ~1e6 triangles
+            v, f, pad, _ = meshgen.tube_lattice(16, 16, 5e-6, 12e-6, 40e-6, 128, 16)
+            n_sv = np.array([100, 100, 50])
+        else:
+            v, f, pad, _ = meshgen.tube_lattice(k, k, 5e-6, 12e-6, 40e-6, 64, 12)
+            n_sv = np.array([50, 50, 50])
         t0 = time.time()
-        sub = substrates.mesh(v, f, True, padding=pad, init_pos="uniform", n_sv=np.array([50, 50, 50]),
-                              quiet=True)
+        sub = substrates.mesh(v, f, True, padding=pad, init_pos="uniform", n_sv=n_sv, quiet=True)
         print("  mesh: %d triangles, %d cell entries, built in %.2f s" % (len(f), len(sub.triangle_indices),
                                                                         time.time() - t0))
         n_t, n = 1000, 1_000_000
