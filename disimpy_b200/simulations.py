@@ -443,8 +443,11 @@ def simulation(
                     sys.stdout.flush()
         elif quiet:
             walk.run(0, n_t)
-        else:  # a handful of launches so that progress can be shown
-            edges = np.unique(np.linspace(0, n_t, min(n_t, 20) + 1).astype(int))
+        else:  # a handful of launches so that progress can be shown (cut on multiples of 8 steps:
+            # the many-measurement kernels work in 8-step chunks)
+            edges = np.linspace(0, n_t, min(n_t, 20) + 1).astype(int)
+            edges[1:-1] = (edges[1:-1] + 4) // 8 * 8
+            edges = np.unique(np.clip(edges, 0, n_t))
             for t0, t1 in zip(edges[:-1], edges[1:]):
                 sys.stdout.write(f"\r{np.round((t0 / n_t) * 100, 1)}%")
                 sys.stdout.flush()
