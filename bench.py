@@ -275,13 +275,14 @@ def main():
     import torch
     import torch.distributed as dist
     import __graft_entry__ as entry
-    if rank == 0:
-        entry.build()
     torch.cuda.set_device(local_rank)
     os.environ["DISIMPY_B200_DEVICE"] = str(local_rank)
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world,
                                 device_id=torch.device("cuda", local_rank))
+    if rank == 0:  # the library ships prebuilt; a missing one is built once, before anybody loads it
+        entry.build(only_if_missing=world > 1)
+    if world > 1:
         dist.barrier()
 
     from disimpy_b200 import _lib, simulations
