@@ -68,7 +68,7 @@ EXPORTS = [
     "dsb_mesh_subdivide_fetch", "dsb_triangle_box_overlap", "dsb_interval_sv_overlap",
     "dsb_host_fill", "dsb_device_count", "dsb_last_error", "dsb_version",
     "dsb_rewind", "dsb_set_positions_part", "dsb_run_part", "dsb_finish", "dsb_release_cache",
-    "dsb_host_sampler_create", "dsb_host_sampler_next", "dsb_host_sampler_destroy",
+    "dsb_set_rng_states", "dsb_host_sampler_create", "dsb_host_sampler_next", "dsb_host_sampler_destroy",
 ]
 
 _lib = None

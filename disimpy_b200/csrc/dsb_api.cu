@@ -737,6 +737,16 @@ DSB_GETTER(dsb_get_phases, double, d_phases, s->prm.n_meas *s->prm.n_walkers)
 DSB_GETTER(dsb_get_iter_exc, uint8_t, d_exc, s->prm.n_walkers)
 DSB_GETTER(dsb_get_rng_states, uint64_t, d_rng, 2 * s->prm.n_walkers)
 
+int dsb_set_rng_states(dsb_sim *s, const uint64_t *states)
+{
+    if (!s || !states) return fail(DSB_EINVAL, "null argument");
+    if (s->t_cur != 0 || s->parts_done != 0) return fail(DSB_ESTATE, "generator states can be replaced at t = 0 only");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    DSB_CUDA(cudaMemcpyAsync(s->d_rng, states, sizeof(uint64_t) * 2 * s->prm.n_walkers, cudaMemcpyHostToDevice, s->stream));
+    DSB_CUDA(cudaStreamSynchronize(s->stream));
+    return DSB_OK;
+}
+
 int dsb_get_run_stats(dsb_sim *s, double *kernel_ms, int64_t *n_launches)
 {
     if (!s) return fail(DSB_EINVAL, "null handle");

@@ -758,7 +758,7 @@ struct ParkFlush {
 template <int SUB, int MR>
 __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR == 0 ? 4 : DSB_MIN_BLOCKS)) walk_kernel(const __grid_constant__ KParams p)
 {
-    __shared__ double s_tab[16];
+    __shared__ __align__(16) double s_tab[16];
     if (threadIdx.x < 16) s_tab[threadIdx.x] = __longlong_as_double((long long)c_sincos_tab[threadIdx.x]);
     __syncthreads();
 

@@ -279,6 +279,10 @@ class Walk:
         _lib.check(self._L.dsb_get_rng_states(self._h, _lib.ptr(out)), "dsb_get_rng_states")
         return out
 
+    def set_rng_states(self, states):
+        st = np.ascontiguousarray(states, dtype=np.uint64)
+        _lib.check(self._L.dsb_set_rng_states(self._h, _lib.ptr(st)), "dsb_set_rng_states")
+
     def run_stats(self):
         ms = ctypes.c_double(0)
         n = ctypes.c_int64(0)
