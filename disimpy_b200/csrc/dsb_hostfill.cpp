@@ -13,42 +13,50 @@
 
 namespace {
 
+// MT19937 that works a whole state at a time: the twist, the tempering and the conversion to
+// 53-bit doubles (genrand_res53, what random_sample() returns: two 32-bit outputs per double) are
+// plain loops over arrays, which the compiler vectorises; the stream is the scalar generator's.
 struct MT19937 {
     uint32_t mt[624];
-    int idx;
+    double buf[312];
+    int pos;
     explicit MT19937(uint32_t seed)
     {
         mt[0] = seed;
         for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
-        idx = 624;
+        pos = 312;
     }
-    static uint32_t twist(uint32_t u, uint32_t v)
+    __attribute__((target_clones("avx2", "default"), optimize("O3"))) void refill()
     {
-        uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
-        return (y >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+        uint32_t *m = mt;
+        for (int k = 0; k < 227; ++k) {
+            uint32_t y = (m[k] & 0x80000000u) | (m[k + 1] & 0x7fffffffu);
+            m[k] = m[k + 397] ^ (y >> 1) ^ ((0u - (m[k + 1] & 1u)) & 0x9908b0dfu);
+        }
+        for (int k = 227; k < 623; ++k) {
+            uint32_t y = (m[k] & 0x80000000u) | (m[k + 1] & 0x7fffffffu);
+            m[k] = m[k - 227] ^ (y >> 1) ^ ((0u - (m[k + 1] & 1u)) & 0x9908b0dfu);
+        }
+        {
+            uint32_t y = (m[623] & 0x80000000u) | (m[0] & 0x7fffffffu);
+            m[623] = m[396] ^ (y >> 1) ^ ((0u - (m[0] & 1u)) & 0x9908b0dfu);
+        }
+        uint32_t t[624];
+        for (int k = 0; k < 624; ++k) {
+            uint32_t y = m[k];
+            y ^= y >> 11;
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= y >> 18;
+            t[k] = y;
+        }
+        for (int k = 0; k < 312; ++k) buf[k] = ((t[2 * k] >> 5) * 67108864.0 + (t[2 * k + 1] >> 6)) / 9007199254740992.0;
+        pos = 0;
     }
-    void refill()
+    double next_double()
     {
-        int k = 0;
-        for (; k < 624 - 397; ++k) mt[k] = mt[k + 397] ^ twist(mt[k], mt[k + 1]);
-        for (; k < 623; ++k) mt[k] = mt[k + 397 - 624] ^ twist(mt[k], mt[k + 1]);
-        mt[623] = mt[396] ^ twist(mt[623], mt[0]);
-        idx = 0;
-    }
-    uint32_t next32()
-    {
-        if (idx >= 624) refill();
-        uint32_t y = mt[idx++];
-        y ^= y >> 11;
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= y >> 18;
-        return y;
-    }
-    double next_double()  // genrand_res53, what random_sample() returns
-    {
-        uint32_t a = next32() >> 5, b = next32() >> 6;
-        return (a * 67108864.0 + b) / 9007199254740992.0;
+        if (pos >= 312) refill();
+        return buf[pos++];
     }
 };
 
@@ -72,11 +80,9 @@ struct dsb_host_sampler {
             while (have < n) {
                 double x = (rng.next_double() - 0.5) * 2 * r;
                 double y = (rng.next_double() - 0.5) * 2 * r;
-                if (std::sqrt(x * x + y * y) < r) {
-                    out[2 * have] = x;
-                    out[2 * have + 1] = y;
-                    ++have;
-                }
+                out[2 * have] = x;  // written unconditionally, kept by advancing: the accept
+                out[2 * have + 1] = y;  // branch is a coin flip the predictor cannot learn
+                have += std::sqrt(x * x + y * y) < r;
             }
         } else if (shape == 1) {
             const double r = scale[0];
@@ -84,12 +90,10 @@ struct dsb_host_sampler {
                 double x = (rng.next_double() - 0.5) * 2 * r;
                 double y = (rng.next_double() - 0.5) * 2 * r;
                 double z = (rng.next_double() - 0.5) * 2 * r;
-                if (std::sqrt(x * x + y * y + z * z) < r) {
-                    out[3 * have] = x;
-                    out[3 * have + 1] = y;
-                    out[3 * have + 2] = z;
-                    ++have;
-                }
+                out[3 * have] = x;
+                out[3 * have + 1] = y;
+                out[3 * have + 2] = z;
+                have += std::sqrt(x * x + y * y + z * z) < r;
             }
         } else {
             const double a = scale[0], b = scale[1], c = scale[2];
@@ -98,12 +102,10 @@ struct dsb_host_sampler {
                 double y = (rng.next_double() - 0.5) * 2 * b;
                 double z = (rng.next_double() - 0.5) * 2 * c;
                 double qx = x / a, qy = y / b, qz = z / c;
-                if (qx * qx + qy * qy + qz * qz < 1) {
-                    out[3 * have] = x;
-                    out[3 * have + 1] = y;
-                    out[3 * have + 2] = z;
-                    ++have;
-                }
+                out[3 * have] = x;
+                out[3 * have + 1] = y;
+                out[3 * have + 2] = z;
+                have += qx * qx + qy * qy + qz * qz < 1;
             }
         }
     }
