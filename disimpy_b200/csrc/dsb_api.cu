@@ -501,12 +501,15 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
     DSB_TRY(cache_malloc(&s->d_exc, N));
     DSB_TRY(cudaMemcpyAsync(s->d_grad, gradient, sizeof(double) * 3 * M * T, cudaMemcpyHostToDevice, s->stream));
     if (M > dsb::kMaxRegMeas) {
-        // chunk-major copy for the many-measurement kernels: (chunk, measurement, step in chunk, xyz)
-        const int64_t C = dsb::kTimeChunk, n_chunks = (T + C - 1) / C;
-        std::vector<double> gc((size_t)(n_chunks * M * C * 3), 0.0);
+        // chunk-major copy for the many-measurement kernels: (chunk, measurement, step in chunk, xyz),
+        // rows padded to kGradRowLen doubles, scaled by gamma * dt (the A operand of the phase GEMM)
+        const int64_t C = dsb::kTimeChunk, L = dsb::kGradRowLen, n_chunks = (T + C - 1) / C;
+        const double gamma_dt = params->dt * 267.513e6;
+        std::vector<double> gc((size_t)(n_chunks * M * L), 0.0);
         for (int64_t m = 0; m < M; ++m)
             for (int64_t t = 0; t < T; ++t)
-                memcpy(&gc[(size_t)((((t / C) * M + m) * C + t % C) * 3)], gradient + (m * T + t) * 3, 3 * sizeof(double));
+                for (int c = 0; c < 3; ++c)
+                    gc[(size_t)(((t / C) * M + m) * L + (t % C) * 3 + c)] = gamma_dt * gradient[(m * T + t) * 3 + c];
         DSB_TRY(cache_malloc(&s->d_grad_chunked, gc.size() * sizeof(double)));
         DSB_TRY(cudaMemcpy(s->d_grad_chunked, gc.data(), gc.size() * sizeof(double), cudaMemcpyHostToDevice));
     }

@@ -14,6 +14,9 @@ namespace dsb {
 #ifndef DSB_MIN_BLOCKS
 #define DSB_MIN_BLOCKS 1
 #endif
+#ifndef DSB_MR0_MIN_BLOCKS
+#define DSB_MR0_MIN_BLOCKS 4
+#endif
 #ifndef DSB_MESH_MIN_BLOCKS
 #define DSB_MESH_MIN_BLOCKS 4
 #endif
@@ -23,7 +26,9 @@ constexpr int kMaxRegMeas = 4;       // measurements whose phase lives in regist
 #define DSB_TIMECHUNK 8
 #endif
 constexpr int kTimeChunk = DSB_TIMECHUNK;  // steps buffered per phase pass when n_meas is larger
-constexpr int kGradRows = 32;              // measurements per gradient tile staged in shared memory
+constexpr int kGradRows = 24;              // measurements per gradient tile staged in shared memory (a multiple of 8)
+constexpr int kGradRowLen = 3 * kTimeChunk + 4;  // doubles per (chunk, measurement) row: 3 per step + padding (bank spread)
+constexpr int kXStride = 36;               // doubles per row of a warp's position tile (32 walkers + padding)
 
 struct MeshDev {
     const double *tri;      // (n_faces, kTriStride): A, B-A, C-A, pad
@@ -614,11 +619,9 @@ __device__ __forceinline__ void mesh_collision(const MeshDev &g, Vec3 &pos, Vec3
 // warp's next search together with the other lanes' next time steps.  Every walker still
 // executes exactly its own sequence of operations (simulations.py:878-1013).
 template <typename Done>
-__device__ __forceinline__ void mesh_walk(const KParams &p, const double *tab, const bool active, const int t_begin,
-                                          const int t_end, Vec3 &pos, Rng &rng, bool &exc, Done done)
+__device__ __forceinline__ void mesh_walk(const KParams &p, MeshScratch &sc, const double *tab, const bool active,
+                                          const int t_begin, const int t_end, Vec3 &pos, Rng &rng, bool &exc, Done done)
 {
-    __shared__ MeshScratch s_scratch[kBlock / 32];
-    MeshScratch &sc = s_scratch[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const MeshDev &g = p.mesh;
     int t = t_begin, iter = 0, closest = 0;
@@ -752,11 +755,20 @@ struct ParkFlush {
     static constexpr int value = SUB == 3 ? DSB_PARK_ELLIPSOID : DSB_PARK;
 };
 
+// D = A * B + C on the FP64 tensor cores: A 8x4 (row major), B 4x8 (column major), C/D 8x8.
+// Lane l holds A[l / 4][l % 4], B[l % 4][l / 4] and C[l / 4][2 * (l % 4) + {0, 1}].
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 // MR > 0: n_meas == MR phases in registers.  MR == 0: any n_meas; positions of kTimeChunk steps
 // are buffered in registers, then each measurement's phase makes one round trip through its
 // (coalesced, L2-resident) row of `phases` per chunk instead of one per step.
 template <int SUB, int MR>
-__global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR == 0 ? 4 : DSB_MIN_BLOCKS)) walk_kernel(const __grid_constant__ KParams p)
+__global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR == 0 ? DSB_MR0_MIN_BLOCKS : DSB_MIN_BLOCKS)) walk_kernel(const __grid_constant__ KParams p)
 {
     __shared__ __align__(16) double s_tab[16];
     if (threadIdx.x < 16) s_tab[threadIdx.x] = __longlong_as_double((long long)c_sincos_tab[threadIdx.x]);
@@ -826,7 +838,8 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                 }
             }
         } else if constexpr (SUB == 4) {
-            mesh_walk(p, s_tab, active, p.t0, p.t1, pos, rng, exc, accumulate);
+            __shared__ MeshScratch s_scratch[kBlock / 32];
+            mesh_walk(p, s_scratch[threadIdx.x >> 5], s_tab, active, p.t0, p.t1, pos, rng, exc, accumulate);
         } else {
             // the time loop is uniform over the block
             for (int t = p.t0; t < p.t1; ++t) {
@@ -851,14 +864,43 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                 return v;
             });
     } else {
+        // Any number of measurements.  The phase update of a chunk of kTimeChunk steps is a matrix
+        // product: Phi[m, i] += sum_k G'[m, k] X[k, i] with G' = gamma dt g (n_meas x 3 kTimeChunk, the
+        // chunk-major gradient copy) and X the positions of the chunk (3 kTimeChunk x walkers).  It
+        // runs on the FP64 tensor cores (mma.sync m8n8k4: the same FLOP/s as DFMA on B200 from an
+        // eighth of the instructions, which is what limited the DFMA version), one warp for its own
+        // 32 walkers:
+        //  * X: every lane writes its walker's positions into the warp's tile in shared memory
+        //    and reads back the 24 B fragments it needs, once per chunk;
+        //  * G': tiles of kGradRows rows are streamed through shared memory by TMA bulk copies
+        //    (double buffered: the next tile, or the next chunk's first tile, travels while this one
+        //    is used); 6 A fragments per 8 measurements;
+        //  * Phi: 8 x 8 accumulator tiles straight from / to the (n_meas, n_walkers) array with
+        //    evict-first accesses, 16 B per lane and tile.
+        // Summation order and roundings differ from the reference's fma chain at the 1e-16 level
+        // (phases for n_meas > 4 agree to ~1e-13, not bit for bit; positions are not affected).
+        // The ragged end of a run (fewer than kTimeChunk steps) uses the reference's formula.
         if (active && p.t0 == 0)
             for (int m = 0; m < p.n_meas; ++m) p.phases[(long long)m * N + w] = 0.0;
-        // positions of one chunk of steps; indexed by the step loop's counter, so it lives in
-        // (L1-resident) local memory rather than in registers: 192 bytes per walker, touched
-        // twice per step, next to 16 * n_meas bytes of phase traffic per chunk
-        Vec3 buf[kTimeChunk];
-        __shared__ __align__(128) double s_grad[2][kGradRows * 3 * kTimeChunk];
+        constexpr int kRows = 3 * kTimeChunk;
+        __shared__ __align__(128) double s_grad[2][kGradRows * kGradRowLen];
         __shared__ unsigned long long s_bar[2];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        // the warp's position tile: rows k = 3 * step + axis, columns = lanes.  The mesh walk keeps
+        // its positions in local memory while it runs (its shared scratch is busy) and the tile
+        // reuses that scratch afterwards.
+        double *xs;
+        Vec3 buf[SUB == 4 ? kTimeChunk : 1];
+        MeshScratch *scratch = nullptr;
+        if constexpr (SUB == 4) {
+            __shared__ MeshScratch s_scratch[kBlock / 32];
+            static_assert(sizeof(MeshScratch) >= sizeof(double) * kRows * kXStride, "position tile must fit the scratch");
+            scratch = &s_scratch[warp];
+            xs = reinterpret_cast<double *>(scratch);
+        } else {
+            __shared__ __align__(16) double s_x[kBlock / 32][kRows * kXStride];
+            xs = s_x[warp];
+        }
         const double *tile = s_grad[0];
         int n_tiles = 0;  // tiles consumed so far by this block (buffer = n_tiles & 1, parity = bit 1)
         if (threadIdx.x == 0) {
@@ -868,79 +910,78 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
         }
         __syncthreads();
         if (threadIdx.x == 0 && p.t0 % kTimeChunk == 0 && p.t1 - p.t0 >= kTimeChunk)  // first tile of the first chunk
-            tma_load_1d(s_grad[0], p.grad_chunked + (long long)(p.t0 / kTimeChunk) * p.n_meas * 3 * kTimeChunk,
-                        min(kGradRows, p.n_meas) * 3 * kTimeChunk * 8, &s_bar[0]);
+            tma_load_1d(s_grad[0], p.grad_chunked + (long long)(p.t0 / kTimeChunk) * p.n_meas * kGradRowLen,
+                        min(kGradRows, p.n_meas) * kGradRowLen * 8, &s_bar[0]);
         for (int t = p.t0; t < p.t1; t += kTimeChunk) {
             const int cnt = min(kTimeChunk, p.t1 - t);
             if constexpr (SUB == 4) {
-                mesh_walk(p, s_tab, active, t, t + cnt, pos, rng, exc, [&](int tt) { buf[tt - t] = pos; });
+                mesh_walk(p, *scratch, s_tab, active, t, t + cnt, pos, rng, exc, [&](int tt) { buf[tt - t] = pos; });
+                __syncwarp();
+                for (int k = 0; k < cnt; ++k) {
+                    xs[(3 * k) * kXStride + lane] = buf[k].x;
+                    xs[(3 * k + 1) * kXStride + lane] = buf[k].y;
+                    xs[(3 * k + 2) * kXStride + lane] = buf[k].z;
+                }
             } else {
 #pragma unroll 1
                 for (int k = 0; k < cnt; ++k) {
                     exc |= time_step<SUB>(pos, rng, p, s_tab, active);
-                    buf[k] = pos;
+                    xs[(3 * k) * kXStride + lane] = pos.x;
+                    xs[(3 * k + 1) * kXStride + lane] = pos.y;
+                    xs[(3 * k + 2) * kXStride + lane] = pos.z;
                 }
             }
+            __syncwarp();
             if (cnt == kTimeChunk && t % kTimeChunk == 0) {
-                // Whole chunk.  The gradient samples of (chunk, measurement) are one row of
-                // 3 * kTimeChunk doubles in chunk-major order; tiles of kGradRows rows are streamed
-                // through shared memory by TMA bulk copies (double buffered: the next tile, or the
-                // next chunk's first tile, travels while this one is used), so every walker of
-                // the block reads them as broadcast LDS.  Phases stream through with evict-first
-                // loads/stores, four measurements per pass, requested one pass ahead.  Per
-                // (measurement, walker) the steps are added in ascending order, like the
-                // reference does launch by launch.
-                Vec3 b[kTimeChunk];
+                const int g8 = lane >> 2, t4 = lane & 3;  // row group and thread-in-group of the mma fragments
+                double bf[kRows / 4][4];                   // B fragments: k-step q, walker tile j
 #pragma unroll
-                for (int k = 0; k < kTimeChunk; ++k) b[k] = buf[k];
-                constexpr int kRowLen = 3 * kTimeChunk;
-                const double *gc = p.grad_chunked + (long long)(t / kTimeChunk) * p.n_meas * kRowLen;
+                for (int q = 0; q < kRows / 4; ++q)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bf[q][j] = xs[(4 * q + t4) * kXStride + 8 * j + g8];
+                const double *gc = p.grad_chunked + (long long)(t / kTimeChunk) * p.n_meas * kGradRowLen;
                 const bool next_chunk = t + 2 * kTimeChunk <= p.t1;
-                double a[4], a_next[4];
-                double *row = p.phases + (active ? w : 0);  // this walker's entry in row m0 (inactive lanes never touch it)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) a_next[j] = (active && j < p.n_meas) ? __ldcs(row + j * N) : 0.0;
-                for (int m0 = 0; m0 < p.n_meas; m0 += 4, row += 4 * N) {
+                const long long w_warp = w - lane;  // first walker of the warp
+                for (int m0 = 0; m0 < p.n_meas; m0 += 8) {
                     if (m0 % kGradRows == 0) {  // next tile
                         const int bufi = n_tiles & 1;
                         __syncthreads();  // everybody is done with the other buffer
                         if (threadIdx.x == 0) {
                             const int m_next = m0 + kGradRows;
                             if (m_next < p.n_meas)
-                                tma_load_1d(s_grad[bufi ^ 1], gc + (long long)m_next * kRowLen,
-                                            min(kGradRows, p.n_meas - m_next) * kRowLen * 8, &s_bar[bufi ^ 1]);
+                                tma_load_1d(s_grad[bufi ^ 1], gc + (long long)m_next * kGradRowLen,
+                                            min(kGradRows, p.n_meas - m_next) * kGradRowLen * 8, &s_bar[bufi ^ 1]);
                             else if (next_chunk)
-                                tma_load_1d(s_grad[bufi ^ 1], gc + (long long)p.n_meas * kRowLen,
-                                            min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[bufi ^ 1]);
+                                tma_load_1d(s_grad[bufi ^ 1], gc + (long long)p.n_meas * kGradRowLen,
+                                            min(kGradRows, p.n_meas) * kGradRowLen * 8, &s_bar[bufi ^ 1]);
                         }
                         mbar_wait(&s_bar[bufi], (n_tiles >> 1) & 1);
                         tile = s_grad[bufi];
                         ++n_tiles;
                     }
-                    const int left = p.n_meas - m0;  // rows from m0 on
+                    const int m = m0 + g8;  // the measurement of this lane's A and C fragments
+                    const bool row_ok = m < p.n_meas;
+                    double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
+                    double c[4][2];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        a[j] = a_next[j];
-                        a_next[j] = (active && 4 + j < left) ? __ldcs(row + (4 + j) * N) : 0.0;
+                        const long long wj = w_warp + 8 * j + 2 * t4;
+                        c[j][0] = (row_ok && wj < p.w_end) ? __ldcs(row + 8 * j) : 0.0;
+                        c[j][1] = (row_ok && wj + 1 < p.w_end) ? __ldcs(row + 8 * j + 1) : 0.0;
                     }
-                    const double2 *g2 = reinterpret_cast<const double2 *>(tile + (m0 % kGradRows) * kRowLen);
+                    const double *arow = tile + ((m0 % kGradRows) + g8) * kGradRowLen + t4;
+                    double af[kRows / 4];
+#pragma unroll
+                    for (int q = 0; q < kRows / 4; ++q) af[q] = row_ok ? arow[4 * q] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < kRows / 4; ++q)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma_m8n8k4(c[j][0], c[j][1], af[q], bf[q][j]);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        if (j < left) {
-                            double g[kRowLen];
-#pragma unroll
-                            for (int q = 0; q < kRowLen / 2; ++q) {
-                                const double2 v = g2[j * (kRowLen / 2) + q];
-                                g[2 * q] = v.x;
-                                g[2 * q + 1] = v.y;
-                            }
-#pragma unroll
-                            for (int k = 0; k < kTimeChunk; ++k)
-                                a[j] = fma_(p.gamma_dt,
-                                            fma_(g[3 * k + 2], b[k].z, fma_(g[3 * k], b[k].x, mul_(g[3 * k + 1], b[k].y))),
-                                            a[j]);
-                            if (active) __stcs(row + j * N, a[j]);
-                        }
+                        const long long wj = w_warp + 8 * j + 2 * t4;
+                        if (row_ok && wj < p.w_end) __stcs(row + 8 * j, c[j][0]);
+                        if (row_ok && wj + 1 < p.w_end) __stcs(row + 8 * j + 1, c[j][1]);
                     }
                 }
             } else if (active) {  // ragged end of the run, or a launch that does not start on a chunk boundary
@@ -950,11 +991,14 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                     const double *g = p.grad + ((long long)m * p.n_t + t) * 3;
                     for (int k = 0; k < cnt; ++k) {
                         double gx = __ldg(g + 3 * k), gy = __ldg(g + 3 * k + 1), gz = __ldg(g + 3 * k + 2);
-                        a = fma_(p.gamma_dt, fma_(gz, buf[k].z, fma_(gx, buf[k].x, mul_(gy, buf[k].y))), a);
+                        const double x = xs[(3 * k) * kXStride + lane], y = xs[(3 * k + 1) * kXStride + lane],
+                                     z = xs[(3 * k + 2) * kXStride + lane];
+                        a = fma_(p.gamma_dt, fma_(gz, z, fma_(gx, x, mul_(gy, y))), a);
                     }
                     *row = a;
                 }
             }
+            __syncwarp();  // the tile is rewritten by the next chunk
         }
         if (active) {
             if (exc) p.iter_exc[w] = 1;
