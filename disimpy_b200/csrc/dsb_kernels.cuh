@@ -942,6 +942,20 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                 const double *gc = p.grad_chunked + (long long)(t / kTimeChunk) * p.n_meas * kGradRowLen;
                 const bool next_chunk = t + 2 * kTimeChunk <= p.t1;
                 const long long w_warp = w - lane;  // first walker of the warp
+                // accumulator tiles are requested one group of 8 measurements ahead (a DRAM round trip each)
+                auto load_c = [&](int m0, double (&c)[4][2]) {
+                    const int m = m0 + g8;
+                    const bool row_ok = m < p.n_meas;
+                    const double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const long long wj = w_warp + 8 * j + 2 * t4;
+                        c[j][0] = (row_ok && wj < p.w_end) ? __ldcs(row + 8 * j) : 0.0;
+                        c[j][1] = (row_ok && wj + 1 < p.w_end) ? __ldcs(row + 8 * j + 1) : 0.0;
+                    }
+                };
+                double c[4][2], c_next[4][2];
+                load_c(0, c_next);
                 for (int m0 = 0; m0 < p.n_meas; m0 += 8) {
                     if (m0 % kGradRows == 0) {  // next tile
                         const int bufi = n_tiles & 1;
@@ -959,16 +973,15 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                         tile = s_grad[bufi];
                         ++n_tiles;
                     }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        c[j][0] = c_next[j][0];
+                        c[j][1] = c_next[j][1];
+                    }
+                    if (m0 + 8 < p.n_meas) load_c(m0 + 8, c_next);
                     const int m = m0 + g8;  // the measurement of this lane's A and C fragments
                     const bool row_ok = m < p.n_meas;
                     double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
-                    double c[4][2];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const long long wj = w_warp + 8 * j + 2 * t4;
-                        c[j][0] = (row_ok && wj < p.w_end) ? __ldcs(row + 8 * j) : 0.0;
-                        c[j][1] = (row_ok && wj + 1 < p.w_end) ? __ldcs(row + 8 * j + 1) : 0.0;
-                    }
                     const double *arow = tile + ((m0 % kGradRows) + g8) * kGradRowLen + t4;
                     double af[kRows / 4];
 #pragma unroll
