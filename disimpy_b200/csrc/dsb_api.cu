@@ -357,6 +357,16 @@ struct dsb_sim {
 
 namespace {
 
+// dynamic shared memory of walk_kernel<SUB, 0> for the analytic substrates: two gradient tiles and
+// one position tile per warp
+template <int SUB>
+constexpr size_t many_meas_smem()
+{
+    return SUB == 4 ? 0
+                    : sizeof(double) * (2 * dsb::kGradRows * dsb::grad_row_len(dsb::ChunkSteps<SUB>::value) +
+                                        (dsb::kBlock / 32) * 3 * dsb::ChunkSteps<SUB>::value * 32);
+}
+
 template <int SUB>
 void launch_walk(const dsb::KParams &kp, int grid, cudaStream_t st)
 {
@@ -365,7 +375,22 @@ void launch_walk(const dsb::KParams &kp, int grid, cudaStream_t st)
     case 2: dsb::walk_kernel<SUB, 2><<<grid, dsb::kBlock, 0, st>>>(kp); break;
     case 3: dsb::walk_kernel<SUB, 3><<<grid, dsb::kBlock, 0, st>>>(kp); break;
     case 4: dsb::walk_kernel<SUB, 4><<<grid, dsb::kBlock, 0, st>>>(kp); break;
-    default: dsb::walk_kernel<SUB, 0><<<grid, dsb::kBlock, 0, st>>>(kp); break;
+    default: {
+        constexpr size_t smem = many_meas_smem<SUB>();
+        if (smem > 48 * 1024) {  // opt in once per device (the attribute is per device and function)
+            static std::mutex mu;
+            static bool done[64] = {false};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            std::lock_guard<std::mutex> lk(mu);
+            if (dev >= 0 && dev < 64 && !done[dev]) {
+                cudaFuncSetAttribute(dsb::walk_kernel<SUB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                done[dev] = true;
+            }
+        }
+        dsb::walk_kernel<SUB, 0><<<grid, dsb::kBlock, smem, st>>>(kp);
+        break;
+    }
     }
 }
 
@@ -503,7 +528,7 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
     if (M > dsb::kMaxRegMeas) {
         // chunk-major copy for the many-measurement kernels: (chunk, measurement, step in chunk, xyz),
         // rows padded to kGradRowLen doubles, scaled by gamma * dt (the A operand of the phase GEMM)
-        const int64_t C = dsb::kTimeChunk, L = dsb::kGradRowLen, n_chunks = (T + C - 1) / C;
+        const int64_t C = dsb::chunk_steps(params->substrate), L = dsb::grad_row_len((int)C), n_chunks = (T + C - 1) / C;
         const double gamma_dt = params->dt * 267.513e6;
         std::vector<double> gc((size_t)(n_chunks * M * L), 0.0);
         for (int64_t m = 0; m < M; ++m)

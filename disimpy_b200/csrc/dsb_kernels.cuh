@@ -22,13 +22,19 @@ namespace dsb {
 #endif
 constexpr int kBlock = DSB_BLOCK;    // threads (= walkers) per CTA
 constexpr int kMaxRegMeas = 4;       // measurements whose phase lives in registers
-#ifndef DSB_TIMECHUNK
-#define DSB_TIMECHUNK 8
+// Steps per chunk of the many-measurement kernels (n_meas > kMaxRegMeas): every phase makes one
+// round trip through HBM per chunk, so longer chunks mean less traffic (16 n_meas / chunk bytes
+// per walker-step); the mesh kernel's shared memory leaves room for 8 steps only.
+template <int SUB>
+struct ChunkSteps {
+    static constexpr int value = SUB == 4 ? 8 : 16;
+};
+__host__ __device__ constexpr int chunk_steps(int substrate) { return substrate == 4 ? 8 : 16; }
+__host__ __device__ constexpr int grad_row_len(int chunk) { return 3 * chunk + 4; }  // + padding (bank spread)
+#ifndef DSB_GRADROWS
+#define DSB_GRADROWS 8
 #endif
-constexpr int kTimeChunk = DSB_TIMECHUNK;  // steps buffered per phase pass when n_meas is larger
-constexpr int kGradRows = 24;              // measurements per gradient tile staged in shared memory (a multiple of 8)
-constexpr int kGradRowLen = 3 * kTimeChunk + 4;  // doubles per (chunk, measurement) row: 3 per step + padding (bank spread)
-constexpr int kXStride = 36;               // doubles per row of a warp's position tile (32 walkers + padding)
+constexpr int kGradRows = DSB_GRADROWS;  // measurements per gradient tile staged in shared memory (a multiple of 8)
 
 struct MeshDev {
     const double *tri;      // (n_faces, kTriStride): A, B-A, C-A, pad
@@ -57,7 +63,7 @@ struct KParams {
     double step_l, gamma_dt, eps, radius;
     double R[9], Rinv[9], ax[3];
     const double *grad;         // (n_meas, n_t, 3)
-    const double *grad_chunked; // (ceil(n_t / kTimeChunk), n_meas, kTimeChunk, 3), zero padded
+    const double *grad_chunked; // (ceil(n_t / chunk), n_meas, grad_row_len(chunk)): gamma dt g, zero padded
     double *pos;                // (n_walkers, 3)
     unsigned long long *rng;    // (n_walkers, 2)
     double *phases;             // (n_meas, n_walkers)
@@ -764,7 +770,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-// MR > 0: n_meas == MR phases in registers.  MR == 0: any n_meas; positions of kTimeChunk steps
+// MR > 0: n_meas == MR phases in registers.  MR == 0: any n_meas; positions of a chunk of steps
 // are buffered in registers, then each measurement's phase makes one round trip through its
 // (coalesced, L2-resident) row of `phases` per chunk instead of one per step.
 template <int SUB, int MR>
@@ -864,44 +870,48 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                 return v;
             });
     } else {
-        // Any number of measurements.  The phase update of a chunk of kTimeChunk steps is a matrix
-        // product: Phi[m, i] += sum_k G'[m, k] X[k, i] with G' = gamma dt g (n_meas x 3 kTimeChunk, the
-        // chunk-major gradient copy) and X the positions of the chunk (3 kTimeChunk x walkers).  It
-        // runs on the FP64 tensor cores (mma.sync m8n8k4: the same FLOP/s as DFMA on B200 from an
-        // eighth of the instructions, which is what limited the DFMA version), one warp for its own
-        // 32 walkers:
+        // Any number of measurements.  The phase update of a chunk of C steps is a matrix product:
+        // Phi[m, i] += sum_k G'[m, k] X[k, i] with G' = gamma dt g (n_meas x 3C, the chunk-major
+        // gradient copy) and X the positions of the chunk (3C x walkers).  It runs on the FP64
+        // tensor cores (mma.sync m8n8k4: the same FLOP/s as DFMA on B200 from an eighth of the
+        // instructions, which is what limited the DFMA version), one warp for its own 32 walkers:
         //  * X: every lane writes its walker's positions into the warp's tile in shared memory
-        //    and reads back the 24 B fragments it needs, once per chunk;
+        //    (swizzled columns: the B fragments are read without bank conflicts);
         //  * G': tiles of kGradRows rows are streamed through shared memory by TMA bulk copies
         //    (double buffered: the next tile, or the next chunk's first tile, travels while this one
-        //    is used); 6 A fragments per 8 measurements;
+        //    is used);
         //  * Phi: 8 x 8 accumulator tiles straight from / to the (n_meas, n_walkers) array with
-        //    evict-first accesses, 16 B per lane and tile.
+        //    evict-first accesses, requested one group of 8 measurements ahead; one round trip
+        //    through HBM per chunk.
         // Summation order and roundings differ from the reference's fma chain at the 1e-16 level
         // (phases for n_meas > 4 agree to ~1e-13, not bit for bit; positions are not affected).
-        // The ragged end of a run (fewer than kTimeChunk steps) uses the reference's formula.
+        // The ragged end of a run (fewer than C steps) uses the reference's formula.
         if (active && p.t0 == 0)
             for (int m = 0; m < p.n_meas; ++m) p.phases[(long long)m * N + w] = 0.0;
-        constexpr int kRows = 3 * kTimeChunk;
-        __shared__ __align__(128) double s_grad[2][kGradRows * kGradRowLen];
-        __shared__ unsigned long long s_bar[2];
+        constexpr int C = ChunkSteps<SUB>::value, kRows = 3 * C, kRowLen = grad_row_len(C);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        // the warp's position tile: rows k = 3 * step + axis, columns = lanes.  The mesh walk keeps
-        // its positions in local memory while it runs (its shared scratch is busy) and the tile
-        // reuses that scratch afterwards.
-        double *xs;
-        Vec3 buf[SUB == 4 ? kTimeChunk : 1];
+        // the warp's position tile: rows k = 3 * step + axis, 32 columns = lanes, column c of row k
+        // kept at c ^ ((k & 3) << 3).  The mesh walk keeps its positions in local memory while it
+        // runs (its shared scratch is busy) and the tile reuses that scratch afterwards; the
+        // analytic kernels get tile and gradient buffers from dynamic shared memory.
+        double *xs, *s_grad;
+        Vec3 buf[SUB == 4 ? C : 1];
         MeshScratch *scratch = nullptr;
+        __shared__ unsigned long long s_bar[2];
         if constexpr (SUB == 4) {
             __shared__ MeshScratch s_scratch[kBlock / 32];
-            static_assert(sizeof(MeshScratch) >= sizeof(double) * kRows * kXStride, "position tile must fit the scratch");
+            __shared__ __align__(128) double s_grad_static[2 * kGradRows * kRowLen];
+            static_assert(sizeof(MeshScratch) >= sizeof(double) * kRows * 32, "position tile must fit the scratch");
             scratch = &s_scratch[warp];
             xs = reinterpret_cast<double *>(scratch);
+            s_grad = s_grad_static;
         } else {
-            __shared__ __align__(16) double s_x[kBlock / 32][kRows * kXStride];
-            xs = s_x[warp];
+            extern __shared__ __align__(128) double s_dyn[];
+            s_grad = s_dyn;
+            xs = s_dyn + 2 * kGradRows * kRowLen + warp * kRows * 32;
         }
-        const double *tile = s_grad[0];
+        auto x_at = [&](int row, int col) -> double & { return xs[row * 32 + (col ^ ((row & 3) << 3))]; };
+        const double *tile = s_grad;
         int n_tiles = 0;  // tiles consumed so far by this block (buffer = n_tiles & 1, parity = bit 1)
         if (threadIdx.x == 0) {
             mbar_init(&s_bar[0], 1);
@@ -909,40 +919,34 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        if (threadIdx.x == 0 && p.t0 % kTimeChunk == 0 && p.t1 - p.t0 >= kTimeChunk)  // first tile of the first chunk
-            tma_load_1d(s_grad[0], p.grad_chunked + (long long)(p.t0 / kTimeChunk) * p.n_meas * kGradRowLen,
-                        min(kGradRows, p.n_meas) * kGradRowLen * 8, &s_bar[0]);
-        for (int t = p.t0; t < p.t1; t += kTimeChunk) {
-            const int cnt = min(kTimeChunk, p.t1 - t);
+        if (threadIdx.x == 0 && p.t0 % C == 0 && p.t1 - p.t0 >= C)  // first tile of the first chunk
+            tma_load_1d(s_grad, p.grad_chunked + (long long)(p.t0 / C) * p.n_meas * kRowLen,
+                        min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[0]);
+        for (int t = p.t0; t < p.t1; t += C) {
+            const int cnt = min(C, p.t1 - t);
             if constexpr (SUB == 4) {
                 mesh_walk(p, *scratch, s_tab, active, t, t + cnt, pos, rng, exc, [&](int tt) { buf[tt - t] = pos; });
                 __syncwarp();
                 for (int k = 0; k < cnt; ++k) {
-                    xs[(3 * k) * kXStride + lane] = buf[k].x;
-                    xs[(3 * k + 1) * kXStride + lane] = buf[k].y;
-                    xs[(3 * k + 2) * kXStride + lane] = buf[k].z;
+                    x_at(3 * k, lane) = buf[k].x;
+                    x_at(3 * k + 1, lane) = buf[k].y;
+                    x_at(3 * k + 2, lane) = buf[k].z;
                 }
             } else {
 #pragma unroll 1
                 for (int k = 0; k < cnt; ++k) {
                     exc |= time_step<SUB>(pos, rng, p, s_tab, active);
-                    xs[(3 * k) * kXStride + lane] = pos.x;
-                    xs[(3 * k + 1) * kXStride + lane] = pos.y;
-                    xs[(3 * k + 2) * kXStride + lane] = pos.z;
+                    x_at(3 * k, lane) = pos.x;
+                    x_at(3 * k + 1, lane) = pos.y;
+                    x_at(3 * k + 2, lane) = pos.z;
                 }
             }
             __syncwarp();
-            if (cnt == kTimeChunk && t % kTimeChunk == 0) {
+            if (cnt == C && t % C == 0) {
                 const int g8 = lane >> 2, t4 = lane & 3;  // row group and thread-in-group of the mma fragments
-                double bf[kRows / 4][4];                   // B fragments: k-step q, walker tile j
-#pragma unroll
-                for (int q = 0; q < kRows / 4; ++q)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) bf[q][j] = xs[(4 * q + t4) * kXStride + 8 * j + g8];
-                const double *gc = p.grad_chunked + (long long)(t / kTimeChunk) * p.n_meas * kGradRowLen;
-                const bool next_chunk = t + 2 * kTimeChunk <= p.t1;
+                const double *gc = p.grad_chunked + (long long)(t / C) * p.n_meas * kRowLen;
+                const bool next_chunk = t + 2 * C <= p.t1;
                 const long long w_warp = w - lane;  // first walker of the warp
-                // accumulator tiles are requested one group of 8 measurements ahead (a DRAM round trip each)
                 auto load_c = [&](int m0, double (&c)[4][2]) {
                     const int m = m0 + g8;
                     const bool row_ok = m < p.n_meas;
@@ -963,14 +967,14 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                         if (threadIdx.x == 0) {
                             const int m_next = m0 + kGradRows;
                             if (m_next < p.n_meas)
-                                tma_load_1d(s_grad[bufi ^ 1], gc + (long long)m_next * kGradRowLen,
-                                            min(kGradRows, p.n_meas - m_next) * kGradRowLen * 8, &s_bar[bufi ^ 1]);
+                                tma_load_1d(s_grad + (bufi ^ 1) * kGradRows * kRowLen, gc + (long long)m_next * kRowLen,
+                                            min(kGradRows, p.n_meas - m_next) * kRowLen * 8, &s_bar[bufi ^ 1]);
                             else if (next_chunk)
-                                tma_load_1d(s_grad[bufi ^ 1], gc + (long long)p.n_meas * kGradRowLen,
-                                            min(kGradRows, p.n_meas) * kGradRowLen * 8, &s_bar[bufi ^ 1]);
+                                tma_load_1d(s_grad + (bufi ^ 1) * kGradRows * kRowLen, gc + (long long)p.n_meas * kRowLen,
+                                            min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[bufi ^ 1]);
                         }
                         mbar_wait(&s_bar[bufi], (n_tiles >> 1) & 1);
-                        tile = s_grad[bufi];
+                        tile = s_grad + bufi * kGradRows * kRowLen;
                         ++n_tiles;
                     }
 #pragma unroll
@@ -982,14 +986,26 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                     const int m = m0 + g8;  // the measurement of this lane's A and C fragments
                     const bool row_ok = m < p.n_meas;
                     double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
-                    const double *arow = tile + ((m0 % kGradRows) + g8) * kGradRowLen + t4;
-                    double af[kRows / 4];
+                    const double *arow = tile + ((m0 % kGradRows) + g8) * kRowLen + t4;
+                    // operands of k-step q + 1 are read from shared memory while the four products of
+                    // k-step q run
+                    double a = row_ok ? arow[0] : 0.0, b[4];
 #pragma unroll
-                    for (int q = 0; q < kRows / 4; ++q) af[q] = row_ok ? arow[4 * q] : 0.0;
+                    for (int j = 0; j < 4; ++j) b[j] = x_at(t4, 8 * j + g8);
 #pragma unroll
-                    for (int q = 0; q < kRows / 4; ++q)
+                    for (int q = 0; q < kRows / 4; ++q) {
+                        double a_next = 0.0, b_next[4] = {0.0, 0.0, 0.0, 0.0};
+                        if (q + 1 < kRows / 4) {
+                            a_next = row_ok ? arow[4 * (q + 1)] : 0.0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dmma_m8n8k4(c[j][0], c[j][1], af[q], bf[q][j]);
+                            for (int j = 0; j < 4; ++j) b_next[j] = x_at(4 * (q + 1) + t4, 8 * j + g8);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma_m8n8k4(c[j][0], c[j][1], a, b[j]);
+                        a = a_next;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) b[j] = b_next[j];
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const long long wj = w_warp + 8 * j + 2 * t4;
@@ -1004,9 +1020,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                     const double *g = p.grad + ((long long)m * p.n_t + t) * 3;
                     for (int k = 0; k < cnt; ++k) {
                         double gx = __ldg(g + 3 * k), gy = __ldg(g + 3 * k + 1), gz = __ldg(g + 3 * k + 2);
-                        const double x = xs[(3 * k) * kXStride + lane], y = xs[(3 * k + 1) * kXStride + lane],
-                                     z = xs[(3 * k + 2) * kXStride + lane];
-                        a = fma_(p.gamma_dt, fma_(gz, z, fma_(gx, x, mul_(gy, y))), a);
+                        a = fma_(p.gamma_dt, fma_(gz, x_at(3 * k + 2, lane), fma_(gx, x_at(3 * k, lane), mul_(gy, x_at(3 * k + 1, lane)))), a);
                     }
                     *row = a;
                 }
