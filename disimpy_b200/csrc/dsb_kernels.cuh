@@ -900,11 +900,10 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
         __shared__ unsigned long long s_bar[2];
         if constexpr (SUB == 4) {
             __shared__ MeshScratch s_scratch[kBlock / 32];
-            __shared__ __align__(128) double s_grad_static[2 * kGradRows * kRowLen];
             static_assert(sizeof(MeshScratch) >= sizeof(double) * kRows * 32, "position tile must fit the scratch");
             scratch = &s_scratch[warp];
             xs = reinterpret_cast<double *>(scratch);
-            s_grad = s_grad_static;
+            s_grad = nullptr;  // the mesh kernel reads the gradient from global memory (see below)
         } else {
             extern __shared__ __align__(128) double s_dyn[];
             s_grad = s_dyn;
@@ -919,7 +918,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        if (threadIdx.x == 0 && p.t0 % C == 0 && p.t1 - p.t0 >= C)  // first tile of the first chunk
+        if (SUB != 4 && threadIdx.x == 0 && p.t0 % C == 0 && p.t1 - p.t0 >= C)  // first tile of the first chunk
             tma_load_1d(s_grad, p.grad_chunked + (long long)(p.t0 / C) * p.n_meas * kRowLen,
                         min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[0]);
         for (int t = p.t0; t < p.t1; t += C) {
@@ -961,7 +960,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                 double c[4][2], c_next[4][2];
                 load_c(0, c_next);
                 for (int m0 = 0; m0 < p.n_meas; m0 += 8) {
-                    if (m0 % kGradRows == 0) {  // next tile
+                    if (SUB != 4 && m0 % kGradRows == 0) {  // next tile
                         const int bufi = n_tiles & 1;
                         __syncthreads();  // everybody is done with the other buffer
                         if (threadIdx.x == 0) {
@@ -986,17 +985,21 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                     const int m = m0 + g8;  // the measurement of this lane's A and C fragments
                     const bool row_ok = m < p.n_meas;
                     double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
-                    const double *arow = tile + ((m0 % kGradRows) + g8) * kRowLen + t4;
+                    // The warps of a mesh block reach this pass at different times (their walks differ),
+                    // so they do not share gradient tiles (that needs block-wide barriers): each reads
+                    // its A fragments from the L1/L2-resident chunk-major copy directly.
+                    const double *arow = SUB == 4 ? gc + (long long)(row_ok ? m : 0) * kRowLen + t4
+                                                  : tile + ((m0 % kGradRows) + g8) * kRowLen + t4;
                     // operands of k-step q + 1 are read from shared memory while the four products of
                     // k-step q run
-                    double a = row_ok ? arow[0] : 0.0, b[4];
+                    double a = row_ok ? (SUB == 4 ? __ldg(arow) : arow[0]) : 0.0, b[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) b[j] = x_at(t4, 8 * j + g8);
 #pragma unroll
                     for (int q = 0; q < kRows / 4; ++q) {
                         double a_next = 0.0, b_next[4] = {0.0, 0.0, 0.0, 0.0};
                         if (q + 1 < kRows / 4) {
-                            a_next = row_ok ? arow[4 * (q + 1)] : 0.0;
+                            a_next = row_ok ? (SUB == 4 ? __ldg(arow + 4 * (q + 1)) : arow[4 * (q + 1)]) : 0.0;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) b_next[j] = x_at(4 * (q + 1) + t4, 8 * j + g8);
                         }
