@@ -37,11 +37,11 @@ def make(case):
                                    utils.vec2vec_rotmat(np.array([1.0, 0, 0]), np.array([1.0, 1.0, 1.0])))
     elif case == "free":
         sub = substrates.free()
-    elif case in ("mesh", "mesh_small", "mesh180", "mesh_big", "mesh_big50", "mesh_coarse", "mesh_verycoarse"):
+    elif case in ("mesh", "mesh_small", "mesh180", "mesh_big", "mesh_big50", "mesh_coarse", "mesh_verycoarse", "config5_shard"):
         k = 2 if case == "mesh_small" else 8
-        if case in ("mesh_big", "mesh_big50"):  # BASELINE config 5's mesh: ~1e6 triangles
+        if case in ("mesh_big", "mesh_big50", "config5_shard"):  # BASELINE config 5's mesh: ~1e6 triangles
             v, f, pad, _ = meshgen.tube_lattice(16, 16, 5e-6, 12e-6, 40e-6, 128, 16)
-            n_sv = np.array([100, 100, 50]) if case == "mesh_big" else np.array([50, 50, 50])
+            n_sv = np.array([50, 50, 50]) if case == "mesh_big50" else np.array([100, 100, 50])
         elif case in ("mesh_coarse", "mesh_verycoarse"):  # the config-4 mesh on coarse grids: long lists per cell
             v, f, pad, _ = meshgen.tube_lattice(k, k, 5e-6, 12e-6, 40e-6, 64, 12)
             n_sv = np.array([16, 16, 8]) if case == "mesh_coarse" else np.array([4, 4, 2])
@@ -55,6 +55,8 @@ def make(case):
         n_t, n = 1000, 1_000_000
         if case == "mesh_verycoarse":
             n_t, n = 100, 100_000
+        if case == "config5_shard":  # a sixth of one GPU's shard of config 5: 2e6 of 1.25e7 walkers, 180 waveforms
+            n_meas, n, n_t = 180, 2_000_000, 1000
         if case == "mesh180":
             n_meas, n = 180, 200_000
     else:
