@@ -957,6 +957,11 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                         c[j][1] = (row_ok && wj + 1 < p.w_end) ? __ldcs(row + 8 * j + 1) : 0.0;
                     }
                 };
+                // B fragment of k-step q and walker tile j: row 4q + t4 (so row & 3 == t4 for every q),
+                // column 8j + g8 -> one pointer per j, the k-step is an immediate offset
+                const double *bcol[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bcol[j] = xs + t4 * 32 + ((8 * j + g8) ^ (t4 << 3));
                 double c[4][2], c_next[4][2];
                 load_c(0, c_next);
                 for (int m0 = 0; m0 < p.n_meas; m0 += 8) {
@@ -994,14 +999,14 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                     // k-step q run
                     double a = row_ok ? (SUB == 4 ? __ldg(arow) : arow[0]) : 0.0, b[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) b[j] = x_at(t4, 8 * j + g8);
+                    for (int j = 0; j < 4; ++j) b[j] = bcol[j][0];
 #pragma unroll
                     for (int q = 0; q < kRows / 4; ++q) {
                         double a_next = 0.0, b_next[4] = {0.0, 0.0, 0.0, 0.0};
                         if (q + 1 < kRows / 4) {
                             a_next = row_ok ? (SUB == 4 ? __ldg(arow + 4 * (q + 1)) : arow[4 * (q + 1)]) : 0.0;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) b_next[j] = x_at(4 * (q + 1) + t4, 8 * j + g8);
+                            for (int j = 0; j < 4; ++j) b_next[j] = bcol[j][128 * (q + 1)];
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) dmma_m8n8k4(c[j][0], c[j][1], a, b[j]);

@@ -3,20 +3,42 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-__global__ void __launch_bounds__(256) dmma_kernel(double *out, int iters, double seed)
+template <int CHAINS>
+__global__ void dmma_kernel(double *out, int iters, double seed)
 {
-    double c[8][2];
-    for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = seed + k;
+    double c[CHAINS][2];
+    for (int k = 0; k < CHAINS; ++k) c[k][0] = c[k][1] = seed + k;
     double a = 1.0000001 + threadIdx.x * 1e-9, b = 0.9999999;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < CHAINS; ++k)
             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                          : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(a), "d"(b));
     }
     double s = 0;
-    for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+    for (int k = 0; k < CHAINS; ++k) s += c[k][0] + c[k][1];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// DMMA rate against the number of independent accumulator chains in flight per SM sub-partition
+template <int CHAINS>
+void sweep(double *out, int sms, cudaEvent_t e0, cudaEvent_t e1)
+{
+    for (int warps_per_smsp = 1; warps_per_smsp <= 8; warps_per_smsp *= 2) {
+        const int threads = 128, blocks = sms * warps_per_smsp, iters = 2048;  // 4 warps per block = 1 per SMSP
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0);
+            dmma_kernel<CHAINS><<<blocks, threads>>>(out, iters, 1.0);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double fma = (double)blocks * threads / 32 * iters * CHAINS * 256.0;
+        printf("DMMA chains/warp %d, warps/SMSP %d: %.2f TFLOP/s\n", CHAINS, warps_per_smsp, 2 * fma / (best * 1e-3) / 1e12);
+    }
 }
 
 __global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, double seed)
@@ -46,7 +68,7 @@ int main()
         float best = 1e30f;
         for (int rep = 0; rep < 4; ++rep) {
             cudaEventRecord(e0);
-            if (which == 0) dmma_kernel<<<blocks, threads>>>(out, iters, 1.0);
+            if (which == 0) dmma_kernel<8><<<blocks, threads>>>(out, iters, 1.0);
             else dfma_kernel<<<blocks, threads>>>(out, iters, 1.0);
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
@@ -60,6 +82,10 @@ int main()
         printf("%s: %.3f ms, %.2f TFLOP/s (2 flop per FMA), %.2f T warp-instr/s\n", which == 0 ? "DMMA m8n8k4" : "DFMA", best,
                2 * fma / (best * 1e-3) / 1e12, warps * iters * 8 / (best * 1e-3) / 1e12);
     }
+    sweep<1>(out, p.multiProcessorCount, e0, e1);
+    sweep<2>(out, p.multiProcessorCount, e0, e1);
+    sweep<4>(out, p.multiProcessorCount, e0, e1);
+    sweep<8>(out, p.multiProcessorCount, e0, e1);
     printf("error state: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
