@@ -202,6 +202,15 @@ def secondary_workloads(device, fp64_peak, sm_mhz):
                  "algorithmic_fp64_instr_per_walker_step": fp64,
                  "fp64_frac": fp64 * rate / fp64_peak,
                  "reference_work_per_walker_step": per}
+        if sub.type == "mesh" and g.shape[0] == 1:
+            # the same workload through the public call: substrate upload, initial positions drawn
+            # on the GPU (init_pos='extra'), walk, signal back
+            simulations.simulation(n, DIFFUSIVITY, g, dt, sub, seed=SEED, quiet=True)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                simulations.simulation(n, DIFFUSIVITY, g, dt, sub, seed=SEED, quiet=True)
+            e2e_s = (time.perf_counter() - t0) / 2
+            entry["e2e"] = {"value": n * g.shape[1] / e2e_s, "unit": UNIT, "ms": 1e3 * e2e_s}
         if sub.type == "mesh":
             l2_peak = L2_PEAK_BYTES_PER_CLK * (sm_mhz or 1965.0) * 1e6
             entry["algorithmic_bytes_per_walker_step"] = nbytes

@@ -68,7 +68,7 @@ EXPORTS = [
     "dsb_mesh_subdivide_fetch", "dsb_triangle_box_overlap", "dsb_interval_sv_overlap",
     "dsb_host_fill", "dsb_device_count", "dsb_last_error", "dsb_version",
     "dsb_rewind", "dsb_set_positions_part", "dsb_run_part", "dsb_finish", "dsb_release_cache",
-    "dsb_set_rng_states", "dsb_host_sampler_create", "dsb_host_sampler_next", "dsb_host_sampler_destroy",
+    "dsb_set_rng_states", "dsb_fill_mesh_sim", "dsb_host_sampler_create", "dsb_host_sampler_next", "dsb_host_sampler_destroy",
 ]
 
 _lib = None
@@ -120,6 +120,19 @@ def lib():
         L.dsb_mesh_subdivide_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.dsb_host_fill.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64,
                                     ctypes.c_void_p, ctypes.c_void_p]
+        L.dsb_rewind.argtypes = [ctypes.c_void_p]
+        L.dsb_finish.argtypes = [ctypes.c_void_p]
+        L.dsb_set_positions_part.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
+        L.dsb_run_part.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]
+        L.dsb_set_rng_states.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.dsb_fill_mesh_sim.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64,
+                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int64]
+        L.dsb_host_sampler_create.argtypes = [ctypes.c_int32, ctypes.c_uint64, ctypes.c_void_p,
+                                              ctypes.POINTER(ctypes.c_void_p)]
+        L.dsb_host_sampler_next.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        L.dsb_host_sampler_destroy.argtypes = [ctypes.c_void_p]
+        L.dsb_release_cache.argtypes = []
+        L.dsb_device_count.argtypes = [ctypes.POINTER(ctypes.c_int32)]
         L.dsb_triangle_box_overlap.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.dsb_interval_sv_overlap.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
                                               ctypes.c_double, c_int64_p, c_int64_p]

@@ -881,6 +881,54 @@ int dsb_rng_states(int32_t device, uint64_t seed, uint64_t subsequence_start, in
     return rc;
 }
 
+int dsb_fill_mesh_sim(dsb_sim *s, const double *voxel_size, int intra, uint64_t seed, int64_t n_points, int64_t first,
+                      int64_t cuda_bs)
+{
+    if (!s || !voxel_size || n_points <= 0 || cuda_bs <= 0 || first < 0) return fail(DSB_EINVAL, "bad arguments");
+    if (s->prm.substrate != DSB_MESH) return fail(DSB_ESTATE, "dsb_fill_mesh_sim needs a mesh handle");
+    if (first + s->prm.n_walkers > n_points || n_points > 0x7fffffffLL) return fail(DSB_EINVAL, "bad point range");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    const int64_t n_states = (n_points + cuda_bs - 1) / cuda_bs * cuda_bs;
+    const int n_blocks = (int)((n_points + dsb::kCompactBlock - 1) / dsb::kCompactBlock);
+    ulonglong2 *d_rng = nullptr;
+    double *d_pts = nullptr;
+    int *d_totals = nullptr;
+    cudaError_t e = cache_malloc(&d_rng, sizeof(ulonglong2) * (size_t)n_states);
+    if (e == cudaSuccess) e = cache_malloc(&d_pts, sizeof(double) * 3 * (size_t)n_points);
+    if (e == cudaSuccess) e = cache_malloc(&d_totals, sizeof(int) * (size_t)(n_blocks + 1));
+    int rc = e == cudaSuccess ? DSB_OK : fail(DSB_ENOMEM, cudaGetErrorString(e));
+    if (!rc) rc = launch_rng_init(s->prm.device, seed, 0, n_states, d_rng, s->stream);
+    int64_t have = 0;
+    // one round per iteration like the reference's host loop (simulations.py:554-579): every
+    // thread proposes a point, the accepted ones are appended in thread order
+    for (int round = 0; !rc && have < n_points; ++round) {
+        if (round > 100000) {
+            rc = fail(DSB_ESTATE, "fill_mesh: no acceptable points (is the surface closed?)");
+            break;
+        }
+        dsb::fill_mesh_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, s->stream>>>(
+            s->mesh.dev, voxel_size[0], voxel_size[1], voxel_size[2], intra, (long long)n_points, d_rng, d_pts);
+        dsb::fill_count_kernel<<<n_blocks, dsb::kCompactBlock, 0, s->stream>>>(d_pts, (long long)n_points, d_totals);
+        dsb::fill_scan_kernel<<<1, 1024, 0, s->stream>>>(d_totals, n_blocks);
+        dsb::fill_scatter_kernel<<<n_blocks, dsb::kCompactBlock, 0, s->stream>>>(
+            d_pts, (long long)n_points, d_totals, (long long)have, (long long)first, (long long)s->prm.n_walkers, s->d_pos);
+        int accepted = 0;
+        e = cudaMemcpyAsync(&accepted, d_totals + n_blocks, sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            rc = fail(DSB_ECUDA, cudaGetErrorString(e));
+            break;
+        }
+        have += accepted;
+    }
+    cache_free(d_rng);
+    cache_free(d_pts);
+    cache_free(d_totals);
+    if (rc) return rc;
+    return rewind_sim(s);
+}
+
 int dsb_fill_mesh(int32_t device, const dsb_mesh *mesh, const double *voxel_size, int intra, uint64_t seed,
                   int64_t n_points, int64_t cuda_bs, double *points)
 {

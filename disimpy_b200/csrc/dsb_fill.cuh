@@ -61,4 +61,85 @@ __global__ void __launch_bounds__(128) fill_mesh_kernel(const MeshDev g, double 
     points[3 * id + 2] = keep ? pt.z : inf;
 }
 
+// ---- keeping the accepted points of a round on the device, in thread order -----------------
+
+constexpr int kCompactBlock = 1024;
+
+// accepted (x != inf) candidates of this block's 1024 candidates: count, and exclusive rank of
+// the calling thread's candidate among them
+__device__ __forceinline__ int block_rank(bool accepted, int &block_total)
+{
+    __shared__ int s_warp[kCompactBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, accepted);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int k = 0; k < kCompactBlock / 32; ++k) {
+        const int c = s_warp[k];
+        before += k < warp ? c : 0;
+        total += c;
+    }
+    __syncthreads();
+    block_total = total;
+    return before + __popc(m & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(kCompactBlock) fill_count_kernel(const double *points, long long n, int *block_totals)
+{
+    const long long i = (long long)blockIdx.x * kCompactBlock + threadIdx.x;
+    const bool ok = i < n && points[3 * i] != __longlong_as_double(0x7FF0000000000000LL);
+    int total;
+    block_rank(ok, total);
+    if (threadIdx.x == 0) block_totals[blockIdx.x] = total;
+}
+
+// exclusive prefix sums of the block totals, in place (one block; every thread takes a
+// contiguous stretch); totals[n_blocks] receives the grand total
+__global__ void __launch_bounds__(1024) fill_scan_kernel(int *totals, int n_blocks)
+{
+    __shared__ long long s_sum[1024];
+    const int per = (n_blocks + 1023) / 1024;
+    const int lo = min(threadIdx.x * per, n_blocks), hi = min(lo + per, n_blocks);
+    long long acc = 0;
+    for (int k = lo; k < hi; ++k) acc += totals[k];
+    s_sum[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        for (int k = 0; k < 1024; ++k) {
+            const long long v = s_sum[k];
+            s_sum[k] = run;
+            run += v;
+        }
+        totals[n_blocks] = (int)run;
+    }
+    __syncthreads();
+    int run = (int)s_sum[threadIdx.x];
+    for (int k = lo; k < hi; ++k) {
+        const int v = totals[k];
+        totals[k] = run;
+        run += v;
+    }
+}
+
+// accepted candidate number r of this round (thread order) becomes global point `have + r`;
+// points [first, first + count) are kept in out (count x 3)
+__global__ void __launch_bounds__(kCompactBlock) fill_scatter_kernel(const double *points, long long n,
+                                                                     const int *block_offsets, long long have,
+                                                                     long long first, long long count, double *out)
+{
+    const long long i = (long long)blockIdx.x * kCompactBlock + threadIdx.x;
+    const bool ok = i < n && points[3 * i] != __longlong_as_double(0x7FF0000000000000LL);
+    int total;
+    const int r = block_rank(ok, total);
+    if (!ok) return;
+    const long long g = have + block_offsets[blockIdx.x] + r - first;
+    if (g >= 0 && g < count) {
+        out[3 * g] = points[3 * i];
+        out[3 * g + 1] = points[3 * i + 1];
+        out[3 * g + 2] = points[3 * i + 2];
+    }
+}
+
 }  // namespace dsb

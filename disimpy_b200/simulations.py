@@ -279,6 +279,14 @@ class Walk:
         _lib.check(self._L.dsb_get_rng_states(self._h, _lib.ptr(out)), "dsb_get_rng_states")
         return out
 
+    def fill_mesh(self, voxel_size, intra, seed, n_points, first, cuda_bs):
+        """Initial positions = points [first, first + n_walkers) of the reference's mesh sampler
+        (simulations.py:505-579), drawn on the GPU against the mesh this handle holds and left
+        there."""
+        voxel = _lib.f64(voxel_size)
+        _lib.check(self._L.dsb_fill_mesh_sim(self._h, _lib.ptr(voxel), 1 if intra else 0, seed, n_points, first,
+                                             cuda_bs), "dsb_fill_mesh_sim")
+
     def set_rng_states(self, states):
         st = np.ascontiguousarray(states, dtype=np.uint64)
         _lib.check(self._L.dsb_set_rng_states(self._h, _lib.ptr(st)), "dsb_set_rng_states")
@@ -393,6 +401,7 @@ def simulation(
     # drawn part by part while the GPU already walks the earlier parts.
     pipelined = substrate.type in ("sphere", "cylinder", "ellipsoid") and not traj and quiet
     positions = None
+    device_fill = False
     if pipelined:
         pass
     elif substrate.type == "free":
@@ -414,6 +423,9 @@ def simulation(
                 print("Calculating initial positions")
             if substrate.init_pos == "uniform":
                 positions = np.random.random((n_walkers, 3)) * substrate.voxel_size
+            elif substrate.periodic:
+                # drawn on the GPU against the mesh the walk's handle holds, and left there
+                device_fill = True
             elif substrate.init_pos == "intra":
                 positions = _fill_mesh(n_walkers, substrate, True, seed, cuda_bs)
             else:
@@ -423,7 +435,7 @@ def simulation(
 
     rank, world, dist = _dist()
     lo, hi = shard_range(n_walkers, rank, world)
-    if traj and rank == 0:
+    if traj and rank == 0 and not device_fill:
         _write_traj(traj, "w", positions)
 
     params, keep = make_params(substrate, hi - lo, lo, gradient, dt, step_l, seed, max_iter,
@@ -432,6 +444,12 @@ def simulation(
     try:
         if pipelined:
             _walk_pipelined(walk, substrate, lo, hi, seed)
+        elif device_fill:
+            walk.fill_mesh(substrate.voxel_size, substrate.init_pos == "intra", seed, n_walkers, lo, cuda_bs)
+            if traj:
+                start = _gather_rows(walk.positions(), n_walkers, lo, hi, dist)
+                if rank == 0:
+                    _write_traj(traj, "w", start)
         else:
             walk.set_positions(positions[lo:hi])
         if pipelined:
