@@ -185,23 +185,47 @@ def secondary_workloads(device, fp64_peak, sm_mhz):
             if mesh_pos is None:
                 mesh_pos = simulations._fill_mesh(n, sub, False, SEED)
             pos = mesh_pos
-        params, keep = simulations.make_params(sub, n, 0, g, dt, step_l, SEED, 1000, 1e-13, device=device)
-        walk = simulations.Walk(params, g)
-        best = None
-        for _ in range(3):
-            walk.set_positions(pos)
-            walk.run()
-            sig, n_valid = walk.signal()
-            ms, _ = walk.run_stats()
-            best = ms if best is None else min(best, ms)
-        walk.close()
-        rate = n * g.shape[1] / (best * 1e-3)
+        def kernel_rate(general_path):
+            """best of 3 launches; general_path: with the low-rank shortcut for PGSE-type protocols off"""
+            if general_path:
+                os.environ["DISIMPY_B200_LOWRANK"] = "0"
+            try:
+                params, keep = simulations.make_params(sub, n, 0, g, dt, step_l, SEED, 1000, 1e-13, device=device)
+                walk = simulations.Walk(params, g)
+            finally:
+                os.environ.pop("DISIMPY_B200_LOWRANK", None)
+            best = None
+            for _ in range(3):
+                walk.set_positions(pos)
+                walk.run()
+                sig, n_valid = walk.signal()
+                ms, _ = walk.run_stats()
+                best = ms if best is None else min(best, ms)
+            rank = walk.protocol_rank()
+            walk.close()
+            return n * g.shape[1] / (best * 1e-3), best, sig, n_valid, rank
+
+        rate, best, sig, n_valid, rank = kernel_rate(False)
         fp64, nbytes, per = algorithmic_work(sub, g, dt, pos=pos)
         entry = {"workload": name, "value": rate, "unit": UNIT, "kernel_ms": best,
                  "signal0_over_n": float(sig[0]) / n, "n_valid": int(n_valid),
                  "algorithmic_fp64_instr_per_walker_step": fp64,
                  "fp64_frac": fp64 * rate / fp64_peak,
                  "reference_work_per_walker_step": per}
+        if rank > 0:
+            # The gradient matrix of this protocol has rank `rank`: the walk carries that many
+            # virtual measurements and expands them at the end, so the reference algorithm's
+            # 4 * n_meas FP64 instructions per walker-step are not executed (fp64_frac, which
+            # credits them, can exceed 1).  The general path is measured next to it.
+            g_rate, g_ms, g_sig, _, _ = kernel_rate(True)
+            fp64_exec = fp64 - W_PHASE * (g.shape[0] - rank)
+            entry["low_rank"] = {"rank": rank, "executed_fp64_instr_per_walker_step": fp64_exec,
+                                 "executed_fp64_frac": fp64_exec * rate / fp64_peak,
+                                 "signal_rel_diff_vs_general_path": float(np.max(np.abs(np.asarray(sig) - np.asarray(g_sig)) /
+                                                                                 np.maximum(np.abs(np.asarray(g_sig)), 1e-300)))}
+            entry["general_path"] = {"value": g_rate, "unit": UNIT, "kernel_ms": g_ms,
+                                     "fp64_frac": fp64 * g_rate / fp64_peak,
+                                     "note": "DISIMPY_B200_LOWRANK=0: phase update as an FP64 tensor-core product"}
         if sub.type == "mesh" and g.shape[0] == 1:
             # the same workload through the public call: substrate upload, initial positions drawn
             # on the GPU (init_pos='extra'), walk, signal back

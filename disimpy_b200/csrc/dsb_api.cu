@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -345,6 +346,8 @@ struct dsb_sim {
     unsigned long long *d_rng = nullptr, *d_rng0 = nullptr;
     unsigned char *d_exc = nullptr;
     MeshBuffers mesh;
+    int rank = 0;            // > 0: low-rank protocol, the walk carries `rank` virtual measurements
+    double *d_u = nullptr;   // (n_meas, rank) coefficients of the real measurements
     int64_t t_cur = -1;  // -1: positions not set
     int64_t parts_done = 0;  // walkers advanced by dsb_run_part since the last rewind
     int grid = 0;
@@ -392,6 +395,78 @@ void launch_walk(const dsb::KParams &kp, int grid, cudaStream_t st)
         break;
     }
     }
+}
+
+// Rank-revealing factorisation of the (M x K) gradient matrix, K = 3 n_t: greedy row-pivoted
+// Gram-Schmidt, at most max_rank steps.  Succeeds when every row lies in the span of the chosen
+// basis up to 1e-13 of the largest row norm; then A = U V with V (rank x K, orthogonal rows
+// scaled to that norm, so that they look like gradients) and U (M x rank).
+bool factor_low_rank(const double *A, int64_t M, int64_t K, int max_rank, std::vector<double> &U, std::vector<double> &V,
+                     int &rank)
+{
+    std::vector<double> R(A, A + M * K), norm2((size_t)M);
+    double top = 0.0;
+    for (int64_t m = 0; m < M; ++m) {
+        double acc = 0.0;
+        for (int64_t k = 0; k < K; ++k) acc += R[m * K + k] * R[m * K + k];
+        norm2[(size_t)m] = acc;
+        top = std::max(top, acc);
+    }
+    if (!(top > 0.0) || !std::isfinite(top)) return false;
+    const double scale = std::sqrt(top), tol2 = 1e-26 * top;
+    std::vector<double> Q, C((size_t)(M * max_rank), 0.0);
+    rank = 0;
+    for (;;) {
+        int64_t piv = 0;
+        for (int64_t m = 1; m < M; ++m)
+            if (norm2[(size_t)m] > norm2[(size_t)piv]) piv = m;
+        if (norm2[(size_t)piv] <= tol2) break;
+        if (rank == max_rank) return false;
+        std::vector<double> q(R.begin() + piv * K, R.begin() + (piv + 1) * K);
+        const double inv = 1.0 / std::sqrt(norm2[(size_t)piv]);
+        for (auto &x : q) x *= inv;
+        for (int pass = 0; pass < 2; ++pass)  // re-orthogonalise against the earlier rows once
+            for (int j = 0; j < rank; ++j) {
+                double d = 0.0;
+                for (int64_t k = 0; k < K; ++k) d += q[(size_t)k] * Q[(size_t)(j * K + k)];
+                for (int64_t k = 0; k < K; ++k) q[(size_t)k] -= d * Q[(size_t)(j * K + k)];
+            }
+        for (int64_t m = 0; m < M; ++m) {
+            double d = 0.0, acc = 0.0;
+            for (int64_t k = 0; k < K; ++k) d += R[m * K + k] * q[(size_t)k];
+            for (int64_t k = 0; k < K; ++k) {
+                R[m * K + k] -= d * q[(size_t)k];
+                acc += R[m * K + k] * R[m * K + k];
+            }
+            C[(size_t)(m * max_rank + rank)] = d;
+            norm2[(size_t)m] = acc;
+        }
+        Q.insert(Q.end(), q.begin(), q.end());
+        ++rank;
+    }
+    if (rank == 0) return false;
+    U.assign((size_t)(M * rank), 0.0);
+    V.assign((size_t)(rank * K), 0.0);
+    for (int j = 0; j < rank; ++j)
+        for (int64_t k = 0; k < K; ++k) V[(size_t)(j * K + k)] = Q[(size_t)(j * K + k)] * scale;
+    // coefficients by projecting the ORIGINAL rows (not the running sums of the elimination)
+    for (int64_t m = 0; m < M; ++m)
+        for (int j = 0; j < rank; ++j) {
+            double d = 0.0;
+            for (int64_t k = 0; k < K; ++k) d += A[m * K + k] * Q[(size_t)(j * K + k)];
+            U[(size_t)(m * rank + j)] = d / scale;
+        }
+    // final check on what will actually be used: |A - U V| row by row
+    for (int64_t m = 0; m < M; ++m) {
+        double acc = 0.0;
+        for (int64_t k = 0; k < K; ++k) {
+            double v = A[m * K + k];
+            for (int j = 0; j < rank; ++j) v -= U[(size_t)(m * rank + j)] * V[(size_t)(j * K + k)];
+            acc += v * v;
+        }
+        if (acc > tol2) return false;
+    }
+    return true;
 }
 
 int check_params(const dsb_params *p, const double *gradient)
@@ -474,6 +549,7 @@ int dsb_destroy(dsb_sim *s)
     cache_free(s->d_phases);
     cache_free(s->d_partials);
     cache_free(s->d_signal);
+    cache_free(s->d_u);
     cache_free(s->d_rng);
     cache_free(s->d_rng0);
     cache_free(s->d_exc);
@@ -516,16 +592,31 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
     DSB_TRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
     DSB_TRY(cudaEventCreateWithFlags(&s->ev_rewind, cudaEventDisableTiming));
     DSB_TRY(cudaEventCreateWithFlags(&s->ev_parts, cudaEventDisableTiming));
-    DSB_TRY(cache_malloc(&s->d_grad, sizeof(double) * 3 * M * T));
+    // Protocols whose gradient matrix has rank <= 4 (all PGSE-type ones) walk with that many virtual
+    // measurements and are expanded at the end; DISIMPY_B200_LOWRANK=0 keeps the general path.
+    std::vector<double> lr_u, lr_v;
+    const char *lr_env = getenv("DISIMPY_B200_LOWRANK");
+    if (M > dsb::kMaxRegMeas && !(lr_env && lr_env[0] == '0') &&
+        factor_low_rank(gradient, M, 3 * T, dsb::kMaxRegMeas, lr_u, lr_v, s->rank)) {
+        gradient = lr_v.data();
+    } else {
+        s->rank = 0;
+    }
+    const int64_t Mw = s->rank > 0 ? s->rank : M;  // measurements the walk kernels see
+    DSB_TRY(cache_malloc(&s->d_grad, sizeof(double) * 3 * Mw * T));
     DSB_TRY(cache_malloc(&s->d_pos, sizeof(double) * 3 * N));
-    DSB_TRY(cache_malloc(&s->d_phases, sizeof(double) * M * N));
+    DSB_TRY(cache_malloc(&s->d_phases, sizeof(double) * Mw * N));
     DSB_TRY(cache_malloc(&s->d_partials, sizeof(double) * (M + 1) * s->grid));
     DSB_TRY(cache_malloc(&s->d_signal, sizeof(double) * (M + 1)));
     DSB_TRY(cache_malloc(&s->d_rng, sizeof(unsigned long long) * 2 * N));
     DSB_TRY(cache_malloc(&s->d_rng0, sizeof(unsigned long long) * 2 * N));
     DSB_TRY(cache_malloc(&s->d_exc, N));
-    DSB_TRY(cudaMemcpyAsync(s->d_grad, gradient, sizeof(double) * 3 * M * T, cudaMemcpyHostToDevice, s->stream));
-    if (M > dsb::kMaxRegMeas) {
+    DSB_TRY(cudaMemcpy(s->d_grad, gradient, sizeof(double) * 3 * Mw * T, cudaMemcpyHostToDevice));
+    if (s->rank > 0) {
+        DSB_TRY(cache_malloc(&s->d_u, sizeof(double) * M * s->rank));
+        DSB_TRY(cudaMemcpy(s->d_u, lr_u.data(), sizeof(double) * M * s->rank, cudaMemcpyHostToDevice));
+    }
+    if (Mw > dsb::kMaxRegMeas) {
         // chunk-major copy for the many-measurement kernels: (chunk, measurement, step in chunk, xyz),
         // rows padded to kGradRowLen doubles, scaled by gamma * dt (the A operand of the phase GEMM)
         const int64_t C = dsb::chunk_steps(params->substrate), L = dsb::grad_row_len((int)C), n_chunks = (T + C - 1) / C;
@@ -604,11 +695,11 @@ static int launch_walk_range(dsb_sim *s, cudaStream_t st, int64_t w0, int64_t w1
     kp.w_begin = w0;
     kp.w_end = w1;
     kp.n_blocks_total = s->grid;
-    kp.n_meas = (int)P.n_meas;
+    kp.n_meas = s->rank > 0 ? s->rank : (int)P.n_meas;
     kp.n_t = (int)P.n_t;
     kp.t0 = (int)t0;
     kp.t1 = (int)t1;
-    kp.finalize = t1 == P.n_t;
+    kp.finalize = t1 == P.n_t && s->rank == 0;  // low-rank protocols are reduced by lowrank_signal_kernel
     kp.max_iter = (int)std::min<int64_t>(P.max_iter, 0x7fffffff);
     kp.step_l = P.step_l;
     kp.gamma_dt = P.dt * 267.513e6;  // dt * GAMMA (gradients.py:13), one rounding like the reference
@@ -650,6 +741,17 @@ static int launch_signal_reduction(dsb_sim *s)
     DSB_CUDA(cudaEventCreate(&e0));
     DSB_CUDA(cudaEventCreate(&e1));
     DSB_CUDA(cudaEventRecord(e0, s->stream));
+    if (s->rank > 0) {
+        dsb::KParams kp{};
+        kp.n_walkers = s->prm.n_walkers;
+        kp.n_blocks_total = s->grid;
+        kp.phases = s->d_phases;
+        kp.iter_exc = s->d_exc;
+        kp.partials = s->d_partials;
+        dsb::lowrank_signal_kernel<<<s->grid, dsb::kBlock, 0, s->stream>>>(kp, s->d_u, s->rank, (int)s->prm.n_meas);
+        DSB_CUDA(cudaGetLastError());
+        s->n_launches += 1;
+    }
     dsb::reduce_partials_kernel<<<(unsigned)(s->prm.n_meas + 1), 256, 0, s->stream>>>(s->d_partials, s->grid, s->d_signal);
     DSB_CUDA(cudaGetLastError());
     DSB_CUDA(cudaEventRecord(e1, s->stream));
@@ -761,7 +863,26 @@ int dsb_get_signal(dsb_sim *s, double *signal, int64_t *n_valid)
     }
 
 DSB_GETTER(dsb_get_positions, double, d_pos, 3 * s->prm.n_walkers)
-DSB_GETTER(dsb_get_phases, double, d_phases, s->prm.n_meas *s->prm.n_walkers)
+int dsb_get_phases(dsb_sim *s, double *dst)
+{
+    if (!s || !dst) return fail(DSB_EINVAL, "null argument");
+    if (s->t_cur < 0) return fail(DSB_ESTATE, "no walker state yet");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    const int64_t N = s->prm.n_walkers, M = s->prm.n_meas;
+    const double *src = s->d_phases;
+    double *d_full = nullptr;
+    if (s->rank > 0) {  // expand the virtual measurements' phases to the real ones
+        DSB_CUDA(cache_malloc(&d_full, sizeof(double) * (size_t)(M * N)));
+        dsb::lowrank_expand_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s->stream>>>(s->d_phases, s->d_u, s->rank, (int)M,
+                                                                                         (long long)N, d_full);
+        src = d_full;
+    }
+    cudaError_t e = cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)(M * N), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cache_free(d_full);
+    if (e != cudaSuccess) return fail(DSB_ECUDA, cudaGetErrorString(e));
+    return DSB_OK;
+}
 DSB_GETTER(dsb_get_iter_exc, uint8_t, d_exc, s->prm.n_walkers)
 DSB_GETTER(dsb_get_rng_states, uint64_t, d_rng, 2 * s->prm.n_walkers)
 
@@ -842,6 +963,7 @@ int dsb_measure_fp64_peak(int32_t device, double *dfma_per_second)
     return DSB_OK;
 }
 
+int dsb_protocol_rank(dsb_sim *s) { return s ? s->rank : 0; }
 void *dsb_stream(dsb_sim *s) { return s ? (void *)s->stream : nullptr; }
 double *dsb_signal_dev(dsb_sim *s) { return s ? s->d_signal : nullptr; }
 

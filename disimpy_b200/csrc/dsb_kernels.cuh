@@ -1051,6 +1051,52 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
     }
 }
 
+// ---------------------------------------------------------------- low-rank protocols
+
+// When the (n_meas x 3 n_t) gradient matrix factors as U V with r <= kMaxRegMeas rows in V (every
+// PGSE-type protocol: one time profile, scaled and rotated per measurement, has rank <= 3), the
+// walk carries the r phases psi of the rows of V in registers and the n_meas real phases are
+// phi[m, i] = sum_k U[m, k] psi[k, i], formed once at the end.
+
+// per-block partial sums of cos(phi) over unflagged walkers (same layout as block_signal writes)
+__global__ void __launch_bounds__(kBlock) lowrank_signal_kernel(const KParams p, const double *u, int rank, int n_real)
+{
+    const long long w = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const bool active = w < p.n_walkers;
+    double psi[kMaxRegMeas];
+#pragma unroll
+    for (int k = 0; k < kMaxRegMeas; ++k) psi[k] = (active && k < rank) ? p.phases[(long long)k * p.n_walkers + w] : 0.0;
+    const bool valid = active && p.iter_exc[w] == 0;
+    KParams q = p;
+    q.n_meas = n_real;
+    q.w_begin = 0;
+    block_signal(q, valid, [&](int m) {
+        double ph = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMaxRegMeas; ++k)
+            if (k < rank) ph = __fma_rn(__ldg(u + (long long)m * rank + k), psi[k], ph);
+        return ph;
+    });
+}
+
+// the (n_real, n_walkers) phase matrix itself, for callers that ask for per-walker output
+__global__ void __launch_bounds__(256) lowrank_expand_kernel(const double *psi, const double *u, int rank, int n_real,
+                                                             long long n_walkers, double *phases)
+{
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_walkers) return;
+    double v[kMaxRegMeas];
+#pragma unroll
+    for (int k = 0; k < kMaxRegMeas; ++k) v[k] = k < rank ? psi[(long long)k * n_walkers + w] : 0.0;
+    for (int m = 0; m < n_real; ++m) {
+        double ph = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMaxRegMeas; ++k)
+            if (k < rank) ph = __fma_rn(__ldg(u + (long long)m * rank + k), v[k], ph);
+        phases[(long long)m * n_walkers + w] = ph;
+    }
+}
+
 // Sums the per-block partials of one measurement (or of the valid-walker count) in a fixed
 // order: thread j takes blocks j, j + 256, ...; then a shared-memory tree.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double *partials, int n_blocks, double *out)

@@ -287,6 +287,11 @@ class Walk:
         _lib.check(self._L.dsb_fill_mesh_sim(self._h, _lib.ptr(voxel), 1 if intra else 0, seed, n_points, first,
                                              cuda_bs), "dsb_fill_mesh_sim")
 
+    def protocol_rank(self):
+        """r > 0: the protocol's gradient matrix has rank r <= 4 and the walk carries r virtual
+        measurements (see include/disimpy_b200.h); 0: general path."""
+        return int(self._L.dsb_protocol_rank(self._h))
+
     def set_rng_states(self, states):
         st = np.ascontiguousarray(states, dtype=np.uint64)
         _lib.check(self._L.dsb_set_rng_states(self._h, _lib.ptr(st)), "dsb_set_rng_states")
