@@ -409,10 +409,11 @@ bool factor_low_rank(const double *A, int64_t M, int64_t K, int max_rank, std::v
     for (int64_t m = 0; m < M; ++m) {
         double acc = 0.0;
         for (int64_t k = 0; k < K; ++k) acc += R[m * K + k] * R[m * K + k];
+        if (!std::isfinite(acc)) return false;  // NaN / inf samples: the general path keeps the reference's semantics
         norm2[(size_t)m] = acc;
         top = std::max(top, acc);
     }
-    if (!(top > 0.0) || !std::isfinite(top)) return false;
+    if (!(top > 0.0)) return false;
     const double scale = std::sqrt(top), tol2 = 1e-26 * top;
     std::vector<double> Q, C((size_t)(M * max_rank), 0.0);
     rank = 0;
@@ -464,7 +465,7 @@ bool factor_low_rank(const double *A, int64_t M, int64_t K, int max_rank, std::v
             for (int j = 0; j < rank; ++j) v -= U[(size_t)(m * rank + j)] * V[(size_t)(j * K + k)];
             acc += v * v;
         }
-        if (acc > tol2) return false;
+        if (!(acc <= tol2)) return false;
     }
     return true;
 }
