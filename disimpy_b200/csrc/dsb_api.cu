@@ -598,8 +598,8 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
     std::vector<double> lr_u, lr_v;
     const char *lr_env = getenv("DISIMPY_B200_LOWRANK");
     if (M > dsb::kMaxRegMeas && !(lr_env && lr_env[0] == '0') &&
-        factor_low_rank(gradient, M, 3 * T, dsb::kMaxRegMeas, lr_u, lr_v, s->rank)) {
-        gradient = lr_v.data();
+        factor_low_rank(gradient, M, 3 * T, (int)std::min<int64_t>(dsb::kMaxRank, M / 2), lr_u, lr_v, s->rank)) {
+        gradient = lr_v.data();  // (a rank above M / 2 would not pay for the expansion)
     } else {
         s->rank = 0;
     }
@@ -622,11 +622,11 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
         // rows padded to kGradRowLen doubles, scaled by gamma * dt (the A operand of the phase GEMM)
         const int64_t C = dsb::chunk_steps(params->substrate), L = dsb::grad_row_len((int)C), n_chunks = (T + C - 1) / C;
         const double gamma_dt = params->dt * 267.513e6;
-        std::vector<double> gc((size_t)(n_chunks * M * L), 0.0);
-        for (int64_t m = 0; m < M; ++m)
+        std::vector<double> gc((size_t)(n_chunks * Mw * L), 0.0);
+        for (int64_t m = 0; m < Mw; ++m)
             for (int64_t t = 0; t < T; ++t)
                 for (int c = 0; c < 3; ++c)
-                    gc[(size_t)(((t / C) * M + m) * L + (t % C) * 3 + c)] = gamma_dt * gradient[(m * T + t) * 3 + c];
+                    gc[(size_t)(((t / C) * Mw + m) * L + (t % C) * 3 + c)] = gamma_dt * gradient[(m * T + t) * 3 + c];
         DSB_TRY(cache_malloc(&s->d_grad_chunked, gc.size() * sizeof(double)));
         DSB_TRY(cudaMemcpy(s->d_grad_chunked, gc.data(), gc.size() * sizeof(double), cudaMemcpyHostToDevice));
     }

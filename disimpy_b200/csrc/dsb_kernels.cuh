@@ -22,6 +22,7 @@ namespace dsb {
 #endif
 constexpr int kBlock = DSB_BLOCK;    // threads (= walkers) per CTA
 constexpr int kMaxRegMeas = 4;       // measurements whose phase lives in registers
+constexpr int kMaxRank = 16;         // largest rank of a protocol walked through virtual measurements
 // Steps per chunk of the many-measurement kernels (n_meas > kMaxRegMeas): every phase makes one
 // round trip through HBM per chunk, so longer chunks mean less traffic (16 n_meas / chunk bytes
 // per walker-step); the mesh kernel's shared memory leaves room for 8 steps only.
@@ -1053,19 +1054,20 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
 
 // ---------------------------------------------------------------- low-rank protocols
 
-// When the (n_meas x 3 n_t) gradient matrix factors as U V with r <= kMaxRegMeas rows in V (every
-// PGSE-type protocol: one time profile, scaled and rotated per measurement, has rank <= 3), the
-// walk carries the r phases psi of the rows of V in registers and the n_meas real phases are
-// phi[m, i] = sum_k U[m, k] psi[k, i], formed once at the end.
+// When the (n_meas x 3 n_t) gradient matrix factors as U V with r <= kMaxRank rows in V (every
+// PGSE-type protocol: one time profile, scaled and rotated per measurement, has rank <= 3; k
+// different timings give rank <= 3k), the walk carries the r phases psi of the rows of V (in
+// registers for r <= kMaxRegMeas, through the many-measurement kernels above that) and the
+// n_meas real phases are phi[m, i] = sum_k U[m, k] psi[k, i], formed once at the end.
 
 // per-block partial sums of cos(phi) over unflagged walkers (same layout as block_signal writes)
 __global__ void __launch_bounds__(kBlock) lowrank_signal_kernel(const KParams p, const double *u, int rank, int n_real)
 {
     const long long w = (long long)blockIdx.x * kBlock + threadIdx.x;
     const bool active = w < p.n_walkers;
-    double psi[kMaxRegMeas];
+    double psi[kMaxRank];
 #pragma unroll
-    for (int k = 0; k < kMaxRegMeas; ++k) psi[k] = (active && k < rank) ? p.phases[(long long)k * p.n_walkers + w] : 0.0;
+    for (int k = 0; k < kMaxRank; ++k) psi[k] = (active && k < rank) ? p.phases[(long long)k * p.n_walkers + w] : 0.0;
     const bool valid = active && p.iter_exc[w] == 0;
     KParams q = p;
     q.n_meas = n_real;
@@ -1073,7 +1075,7 @@ __global__ void __launch_bounds__(kBlock) lowrank_signal_kernel(const KParams p,
     block_signal(q, valid, [&](int m) {
         double ph = 0.0;
 #pragma unroll
-        for (int k = 0; k < kMaxRegMeas; ++k)
+        for (int k = 0; k < kMaxRank; ++k)
             if (k < rank) ph = __fma_rn(__ldg(u + (long long)m * rank + k), psi[k], ph);
         return ph;
     });
@@ -1085,13 +1087,13 @@ __global__ void __launch_bounds__(256) lowrank_expand_kernel(const double *psi, 
 {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_walkers) return;
-    double v[kMaxRegMeas];
+    double v[kMaxRank];
 #pragma unroll
-    for (int k = 0; k < kMaxRegMeas; ++k) v[k] = k < rank ? psi[(long long)k * n_walkers + w] : 0.0;
+    for (int k = 0; k < kMaxRank; ++k) v[k] = k < rank ? psi[(long long)k * n_walkers + w] : 0.0;
     for (int m = 0; m < n_real; ++m) {
         double ph = 0.0;
 #pragma unroll
-        for (int k = 0; k < kMaxRegMeas; ++k)
+        for (int k = 0; k < kMaxRank; ++k)
             if (k < rank) ph = __fma_rn(__ldg(u + (long long)m * rank + k), v[k], ph);
         phases[(long long)m * n_walkers + w] = ph;
     }
