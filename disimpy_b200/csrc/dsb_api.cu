@@ -786,6 +786,15 @@ int dsb_rewind(dsb_sim *s)
     return rewind_sim(s);
 }
 
+int dsb_set_rng_part(dsb_sim *s, int64_t w0, int64_t w1, int64_t global_offset)
+{
+    if (!s) return fail(DSB_EINVAL, "null handle");
+    if (w0 < 0 || w1 <= w0 || w1 > s->prm.n_walkers || global_offset < 0) return fail(DSB_EINVAL, "bad walker range");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    return launch_rng_init(s->prm.device, s->prm.seed, (uint64_t)global_offset, w1 - w0,
+                           reinterpret_cast<ulonglong2 *>(s->d_rng0) + w0, s->stream);
+}
+
 int dsb_set_positions_part(dsb_sim *s, int64_t w0, int64_t w1, const double *positions)
 {
     if (!s || !positions) return fail(DSB_EINVAL, "null argument");

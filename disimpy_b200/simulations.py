@@ -182,6 +182,26 @@ def shard_range(n_walkers, rank, world_size):
     return n_walkers * rank // world_size, n_walkers * (rank + 1) // world_size
 
 
+def owned_ranges(n_walkers, rank, world_size, interleaved=False, part=None):
+    """Which global walkers a rank holds and where: [(global_lo, global_hi, local_lo), ...].
+
+    Contiguous (default): the one range of shard_range.  Interleaved: the parts of ``part``
+    walkers are dealt round-robin to the ranks -- used when the initial positions come from the
+    sequential host stream, so that every rank can start on its first part after 1/world_size of
+    the wait a contiguous shard at the end of the stream would have."""
+    if not interleaved:
+        lo, hi = shard_range(n_walkers, rank, world_size)
+        return [(lo, hi, 0)]
+    part = _PART if part is None else part
+    out, local = [], 0
+    for k, a in enumerate(range(0, n_walkers, part)):
+        if k % world_size == rank:
+            b = min(a + part, n_walkers)
+            out.append((a, b, local))
+            local += b - a
+    return out
+
+
 def make_params(substrate, n_walkers, walker_offset, gradient, dt, step_l, seed, max_iter,
                 epsilon, device=None):
     """Fill the C ABI's dsb_params for one shard; returns (params, keep_alive)."""
@@ -248,6 +268,10 @@ class Walk:
 
     def finish(self):
         _lib.check(self._L.dsb_finish(self._h), "dsb_finish")
+
+    def set_rng_part(self, w0, w1, global_offset):
+        """Local walkers [w0, w1) are the global walkers global_offset ... (their RNG subsequences)."""
+        _lib.check(self._L.dsb_set_rng_part(self._h, w0, w1, global_offset), "dsb_set_rng_part")
 
     def sync(self):
         _lib.check(self._L.dsb_sync(self._h), "dsb_sync")
@@ -439,20 +463,27 @@ def simulation(
                 print("Finished calculating initial positions")
 
     rank, world, dist = _dist()
-    lo, hi = shard_range(n_walkers, rank, world)
+    # the parts of a pipelined run are dealt round-robin to the ranks (if there are enough of them)
+    interleaved = pipelined and world > 1 and (n_walkers + _PART - 1) // _PART >= world
+    owned = owned_ranges(n_walkers, rank, world, interleaved)
+    lo, hi = owned[0][0], owned[0][1]          # (the contiguous shard when not interleaved)
+    n_local = sum(b - a for a, b, _ in owned)
     if traj and rank == 0 and not device_fill:
         _write_traj(traj, "w", positions)
 
-    params, keep = make_params(substrate, hi - lo, lo, gradient, dt, step_l, seed, max_iter,
+    params, keep = make_params(substrate, n_local, lo, gradient, dt, step_l, seed, max_iter,
                                epsilon)
     walk = Walk(params, gradient)
     try:
+        if interleaved:
+            for a, b, la in owned:
+                walk.set_rng_part(la, la + b - a, a)
         if pipelined:
-            _walk_pipelined(walk, substrate, lo, hi, seed)
+            _walk_pipelined(walk, substrate, owned, seed)
         elif device_fill:
             walk.fill_mesh(substrate.voxel_size, substrate.init_pos == "intra", seed, n_walkers, lo, cuda_bs)
             if traj:
-                start = _gather_rows(walk.positions(), n_walkers, lo, hi, dist)
+                start = _gather_rows(walk.positions(), n_walkers, owned, dist)
                 if rank == 0:
                     _write_traj(traj, "w", start)
         else:
@@ -462,7 +493,7 @@ def simulation(
         elif traj:
             for t in range(n_t):
                 walk.run(t, t + 1)
-                step_pos = _gather_rows(walk.positions(), n_walkers, lo, hi, dist)
+                step_pos = _gather_rows(walk.positions(), n_walkers, owned, dist)
                 if rank == 0:
                     _write_traj(traj, "a", step_pos)
                 if not quiet:
@@ -489,14 +520,14 @@ def simulation(
             n_flagged = int(iter_exc.sum())
         else:
             signals, n_valid = walk.signal()
-            n_flagged = (hi - lo) - n_valid
+            n_flagged = n_local - n_valid
             iter_exc = None
         if dist is not None:
             n_flagged = int(round(_allreduce_sum(np.array([float(n_flagged)]), dist)[0]))
         if n_flagged > 0:
             if iter_exc is None:
                 iter_exc = walk.iter_exc()
-            iter_exc_all = _gather_rows(iter_exc, n_walkers, lo, hi, dist)
+            iter_exc_all = _gather_rows(iter_exc, n_walkers, owned, dist)
             warnings.warn(
                 "Maximum number of iterations was exceeded in the intersection "
                 + "check algorithm for walkers %s" % np.where(iter_exc_all)[0])
@@ -505,14 +536,14 @@ def simulation(
             phases = walk.phases()
             phases[:, np.where(iter_exc)[0]] = np.nan
             signals = np.real(np.exp(1j * phases))
-            signals = _gather_rows(signals.T, n_walkers, lo, hi, dist).T
+            signals = _gather_rows(signals.T, n_walkers, owned, dist).T
         elif dist is not None:
             signals = _allreduce_sum(signals, dist)
         if not quiet:
             sys.stdout.write("\rSimulation finished\n")
             sys.stdout.flush()
         if final_pos:
-            final = _gather_rows(walk.positions(), n_walkers, lo, hi, dist)
+            final = _gather_rows(walk.positions(), n_walkers, owned, dist)
             return signals, final
         return signals
     finally:
@@ -522,11 +553,12 @@ def simulation(
 _PART = 131072  # walkers per part: about one full wave of 128-walker blocks on a B200
 
 
-def _position_parts(substrate, lo, hi, seed, part=_PART):
+def _position_parts(substrate, lo, hi, seed, part=_PART, wanted=None):
     """Initial positions of global walkers [lo, hi) of an analytic substrate, part by part:
     yields (a, b, positions of local walkers [a, b)).  Concatenated, the parts are what
     _fill_sphere / _initial_positions_cylinder / _initial_positions_ellipsoid return in one go
-    (simulations.py:346-418)."""
+    (simulations.py:346-418).  Parts for which ``wanted(a, b)`` is false are drawn (the stream is
+    sequential) but not yielded."""
     if substrate.type == "sphere":
         sampler, to_lab = _HostSampler(1, seed, substrate.radius, 3), None
     elif substrate.type == "cylinder":
@@ -540,6 +572,8 @@ def _position_parts(substrate, lo, hi, seed, part=_PART):
         for a in range(0, n, part):
             b = min(a + part, n)
             pts = sampler.next(b - a)
+            if wanted is not None and not wanted(a, b):
+                continue
             if substrate.type == "cylinder":
                 body = np.zeros((b - a, 3))
                 body[:, 1:3] = pts
@@ -551,14 +585,22 @@ def _position_parts(substrate, lo, hi, seed, part=_PART):
         sampler.close()
 
 
-def _walk_pipelined(walk, substrate, lo, hi, seed):
+def _walk_pipelined(walk, substrate, owned, seed):
     """Walks every part over all time steps as soon as its positions are there: the host draws
     the next part while the GPU works.  Same positions, same walk, same signal as drawing
-    everything first."""
+    everything first.  ``owned``: the rank's walkers (owned_ranges)."""
     walk.rewind()
-    for a, b, pts in _position_parts(substrate, lo, hi, seed):
-        walk.set_positions_part(a, b, pts)
-        walk.run_part(a, b)
+    if len(owned) == 1:   # one contiguous shard: skip to it, then part by part
+        lo, hi, _ = owned[0]
+        for a, b, pts in _position_parts(substrate, lo, hi, seed):
+            walk.set_positions_part(a, b, pts)
+            walk.run_part(a, b)
+    else:                 # parts dealt round-robin: draw the whole stream, keep this rank's parts
+        local_of = {a: la for a, _, la in owned}
+        for a, b, pts in _position_parts(substrate, 0, owned[-1][1], seed, wanted=lambda a, b: a in local_of):
+            la = local_of[a]
+            walk.set_positions_part(la, la + b - a, pts)
+            walk.run_part(la, la + b - a)
     walk.finish()
 
 
@@ -571,15 +613,16 @@ def _allreduce_sum(values, dist):
     return t.cpu().numpy()
 
 
-def _gather_rows(local, n_total, lo, hi, dist):
+def _gather_rows(local, n_total, owned, dist):
     """Assemble per-walker rows from all ranks (only used for final_pos / all_signals / traj
-    / the iter_exc warning -- per-shard host gathers, no device collective)."""
+    / the iter_exc warning -- per-shard host gathers, no device collective).  ``owned``: this
+    rank's walkers as owned_ranges returns them."""
     if dist is None:
         return local
-    import torch
     out = [None] * dist.get_world_size()
-    dist.all_gather_object(out, (lo, hi, local))
+    dist.all_gather_object(out, (owned, local))
     full = np.zeros((n_total,) + local.shape[1:], dtype=local.dtype)
-    for a, b, part in out:
-        full[a:b] = part
+    for ranges, rows in out:
+        for a, b, la in ranges:
+            full[a:b] = rows[la:la + b - a]
     return full

@@ -301,10 +301,22 @@ pos0 = O.initial_positions(sub, n, 9)
 part = O.run_walk(sub, grad, 1e-4, 2e-9, pos0[lo:hi], seed=9, walker_offset=lo)
 sig = O.signals_from_phases(part["phases"], part["iter_exc"])
 total = simulations._allreduce_sum(sig, d)
-allpos = simulations._gather_rows(part["positions"], n, lo, hi, d)
+allpos = simulations._gather_rows(part["positions"], n, simulations.owned_ranges(n, rank, world), d)
 full = O.run_walk(sub, grad, 1e-4, 2e-9, pos0, seed=9)
 assert np.array_equal(allpos, full["positions"])
 assert np.allclose(total, O.signals_from_phases(full["phases"], full["iter_exc"]), rtol=1e-13)
+# the round-robin deal of parts (what a pipelined multi-GPU simulation() uses): every part with its
+# own RNG offset, rows gathered back into global order
+owned = simulations.owned_ranges(n, rank, world, interleaved=True, part=64)
+assert sum(b - a for a, b, _ in owned) > 0 and [la for _, _, la in owned][0] == 0
+rows = np.zeros((sum(b - a for a, b, _ in owned), 3))
+sig2 = np.zeros(3)
+for a, b, la in owned:
+    piece = O.run_walk(sub, grad, 1e-4, 2e-9, pos0[a:b], seed=9, walker_offset=a)
+    rows[la:la + b - a] = piece["positions"]
+    sig2 += O.signals_from_phases(piece["phases"], piece["iter_exc"])
+assert np.array_equal(simulations._gather_rows(rows, n, owned, d), full["positions"])
+assert np.allclose(simulations._allreduce_sum(sig2, d), O.signals_from_phases(full["phases"], full["iter_exc"]), rtol=1e-13)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
@@ -347,3 +359,17 @@ def test_position_parts_equal_one_shot_sampling():
             assert [a for a, _, _ in parts] == list(range(0, hi - lo, 65_536))
             got = np.vstack([pts for _, _, pts in parts])
             assert np.array_equal(got, full[lo:hi]), sub.type
+
+
+def test_round_robin_parts_cover_all_walkers():
+    from disimpy_b200 import simulations
+    for n, world, part in ((1000, 3, 64), (131072 * 5 + 17, 2, None), (64, 4, 64), (10, 1, 4)):
+        seen = np.zeros(n, dtype=int)
+        for rank in range(world):
+            owned = simulations.owned_ranges(n, rank, world, interleaved=True, part=part)
+            local = 0
+            for a, b, la in owned:
+                assert la == local and 0 <= a < b <= n
+                seen[a:b] += 1
+                local += b - a
+        assert np.all(seen == 1)
