@@ -370,14 +370,14 @@ constexpr size_t many_meas_smem()
                                         (dsb::kBlock / 32) * 3 * dsb::ChunkSteps<SUB>::value * 32);
 }
 
-template <int SUB>
-void launch_walk(const dsb::KParams &kp, int grid, cudaStream_t st)
+template <int SUB, int MAXC>
+void launch_walk_cells(const dsb::KParams &kp, int grid, cudaStream_t st)
 {
     switch (kp.n_meas <= dsb::kMaxRegMeas ? kp.n_meas : 0) {
-    case 1: dsb::walk_kernel<SUB, 1><<<grid, dsb::kBlock, 0, st>>>(kp); break;
-    case 2: dsb::walk_kernel<SUB, 2><<<grid, dsb::kBlock, 0, st>>>(kp); break;
-    case 3: dsb::walk_kernel<SUB, 3><<<grid, dsb::kBlock, 0, st>>>(kp); break;
-    case 4: dsb::walk_kernel<SUB, 4><<<grid, dsb::kBlock, 0, st>>>(kp); break;
+    case 1: dsb::walk_kernel<SUB, 1, MAXC><<<grid, dsb::kBlock, 0, st>>>(kp); break;
+    case 2: dsb::walk_kernel<SUB, 2, MAXC><<<grid, dsb::kBlock, 0, st>>>(kp); break;
+    case 3: dsb::walk_kernel<SUB, 3, MAXC><<<grid, dsb::kBlock, 0, st>>>(kp); break;
+    case 4: dsb::walk_kernel<SUB, 4, MAXC><<<grid, dsb::kBlock, 0, st>>>(kp); break;
     default: {
         constexpr size_t smem = many_meas_smem<SUB>();
         if (smem > 48 * 1024) {  // opt in once per device (the attribute is per device and function)
@@ -387,14 +387,30 @@ void launch_walk(const dsb::KParams &kp, int grid, cudaStream_t st)
             cudaGetDevice(&dev);
             std::lock_guard<std::mutex> lk(mu);
             if (dev >= 0 && dev < 64 && !done[dev]) {
-                cudaFuncSetAttribute(dsb::walk_kernel<SUB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(dsb::walk_kernel<SUB, 0, MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 done[dev] = true;
             }
         }
-        dsb::walk_kernel<SUB, 0><<<grid, dsb::kBlock, smem, st>>>(kp);
+        dsb::walk_kernel<SUB, 0, MAXC><<<grid, dsb::kBlock, smem, st>>>(kp);
         break;
     }
     }
+}
+
+template <int SUB>
+void launch_walk(const dsb::KParams &kp, int grid, cudaStream_t st)
+{
+    if constexpr (SUB == 4) {
+        // a step shorter than the smallest grid spacing overlaps at most 2 cells per axis: the
+        // kernel variant with 8 cell slots per walker does the same work with shorter loops
+        const dsb::MeshDev &g = kp.mesh;
+        const double h_min = 1.0 / std::max(g.inv_hx, std::max(g.inv_hy, g.inv_hz));
+        if (kp.step_l < h_min) {
+            launch_walk_cells<4, dsb::kMaxCellsShortStep>(kp, grid, st);
+            return;
+        }
+    }
+    launch_walk_cells<SUB, dsb::kMaxCells>(kp, grid, st);
 }
 
 // Rank-revealing factorisation of the (M x K) gradient matrix, K = 3 n_t: greedy row-pivoted

@@ -326,10 +326,10 @@ static_assert(kSurvivorCap * sizeof(double) <= kRangeCap * sizeof(uint4), "hit[]
 __device__ __forceinline__ int quantize(double x, double scale) { return __double2int_rd(x * scale); }
 __device__ __forceinline__ unsigned clamp15(int q) { return (unsigned)min(max(q, 0), 32767); }
 
-#ifndef DSB_MAXCELLS
-#define DSB_MAXCELLS 12
-#endif
-constexpr int kMaxCells = DSB_MAXCELLS;  // cells per walker and search the cooperative path takes
+// Cells per walker and search the cooperative path takes (template parameter of the mesh
+// kernels): 12 in general; 8 when the step is shorter than the smallest grid spacing, so that a
+// segment never overlaps more than 2 cells per axis (the host picks, launch_walk).
+constexpr int kMaxCells = 12, kMaxCellsShortStep = 8;
 
 // c-th cell (visiting order x -> y -> z) of the spans: place of its list range, image flags
 struct CellWalk {
@@ -407,6 +407,7 @@ __device__ __noinline__ void mesh_closest_hit_alone(const MeshDev &g, const Vec3
 // filter only ever errs on the side of keeping a triangle).  The lists of all 32 walkers are
 // numbered through and filtered 32 entries at a time (coalesced), the survivors are compacted
 // (ballot) and tested exactly, again 32 at a time.
+template <int MAXC>
 __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &sc, const int lane, const bool need,
                                                  const Vec3 &pos, const Vec3 &s, const double step_l,
                                                  double &min_d, int &closest)
@@ -432,18 +433,18 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         fast &= axis_span(g.ys, g.len_ys - 1, g.vox[1], g.inv_vox[1], g.inv_hy, pos.y, ey, sy);
         fast &= axis_span(g.zs, g.len_zs - 1, g.vox[2], g.inv_vox[2], g.inv_hz, pos.z, ez, sz);
         n_cells = sx.count * sy.count * sz.count;
-        fast = fast && n_cells <= kMaxCells;
+        fast = fast && n_cells <= MAXC;
     }
     // list ranges of this lane's cells: independent loads, all in flight together; the loops
     // stop at the largest cell count of the warp
     const int n_cells_warp = __reduce_max_sync(full, fast ? n_cells : 0);
-    int2 rng[kMaxCells];
+    int2 rng[MAXC];
 #pragma unroll
-    for (int c = 0; c < kMaxCells; ++c) rng[c] = make_int2(0, 0);
+    for (int c = 0; c < MAXC; ++c) rng[c] = make_int2(0, 0);
     {
         CellWalk cw;
 #pragma unroll
-        for (int c = 0; c < kMaxCells; ++c) {
+        for (int c = 0; c < MAXC; ++c) {
             if (c >= n_cells_warp) break;
             if (fast && c < n_cells) {
                 int flags;
@@ -452,7 +453,7 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
             cw.next(sy, sz);
         }
 #pragma unroll
-        for (int c = 0; c < kMaxCells; ++c) {
+        for (int c = 0; c < MAXC; ++c) {
             n_ranges += rng[c].y > rng[c].x;
             n_entries += rng[c].y - rng[c].x;
         }
@@ -496,7 +497,7 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         int k = incl_r - n_ranges, first = incl_e - n_entries;
         CellWalk cw;
 #pragma unroll
-        for (int c = 0; c < kMaxCells; ++c) {
+        for (int c = 0; c < MAXC; ++c) {
             if (c >= n_cells_warp) break;
             const int n = rng[c].y - rng[c].x;
             if (n > 0) {
@@ -625,7 +626,7 @@ __device__ __forceinline__ void mesh_collision(const MeshDev &g, Vec3 &pos, Vec3
 // therefore not kept in lock step: a walker that bounced stays in flight and takes part in the
 // warp's next search together with the other lanes' next time steps.  Every walker still
 // executes exactly its own sequence of operations (simulations.py:878-1013).
-template <typename Done>
+template <int MAXC, typename Done>
 __device__ __forceinline__ void mesh_walk(const KParams &p, MeshScratch &sc, const double *tab, const bool active,
                                           const int t_begin, const int t_end, Vec3 &pos, Rng &rng, bool &exc, Done done)
 {
@@ -647,7 +648,7 @@ __device__ __forceinline__ void mesh_walk(const KParams &p, MeshScratch &sc, con
         const bool need = in_flight && step_l > 0 && iter < p.max_iter;
         if (need) ++iter;
         double min_d;
-        mesh_closest_hit(g, sc, lane, need, pos, s, step_l, min_d, closest);
+        mesh_closest_hit<MAXC>(g, sc, lane, need, pos, s, step_l, min_d, closest);
         if (in_flight) {
             if (need && !(min_d > step_l)) {
                 mesh_collision(g, pos, s, rng, min_d, closest, p.eps);
@@ -774,7 +775,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 // MR > 0: n_meas == MR phases in registers.  MR == 0: any n_meas; positions of a chunk of steps
 // are buffered in registers, then each measurement's phase makes one round trip through its
 // (coalesced, L2-resident) row of `phases` per chunk instead of one per step.
-template <int SUB, int MR>
+template <int SUB, int MR, int MAXC = kMaxCells>
 __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR == 0 ? DSB_MR0_MIN_BLOCKS : DSB_MIN_BLOCKS)) walk_kernel(const __grid_constant__ KParams p)
 {
     __shared__ __align__(16) double s_tab[16];
@@ -846,7 +847,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
             }
         } else if constexpr (SUB == 4) {
             __shared__ MeshScratch s_scratch[kBlock / 32];
-            mesh_walk(p, s_scratch[threadIdx.x >> 5], s_tab, active, p.t0, p.t1, pos, rng, exc, accumulate);
+            mesh_walk<MAXC>(p, s_scratch[threadIdx.x >> 5], s_tab, active, p.t0, p.t1, pos, rng, exc, accumulate);
         } else {
             // the time loop is uniform over the block
             for (int t = p.t0; t < p.t1; ++t) {
@@ -925,7 +926,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
         for (int t = p.t0; t < p.t1; t += C) {
             const int cnt = min(C, p.t1 - t);
             if constexpr (SUB == 4) {
-                mesh_walk(p, *scratch, s_tab, active, t, t + cnt, pos, rng, exc, [&](int tt) { buf[tt - t] = pos; });
+                mesh_walk<MAXC>(p, *scratch, s_tab, active, t, t + cnt, pos, rng, exc, [&](int tt) { buf[tt - t] = pos; });
                 __syncwarp();
                 for (int k = 0; k < cnt; ++k) {
                     x_at(3 * k, lane) = buf[k].x;
