@@ -1,0 +1,104 @@
+"""The reference's own end-to-end tests (disimpy/tests/test_simulations.py:460-683), run against
+this package on the GPU with the reference's tolerances: analytic free diffusion, MISST signals
+for sphere and cylinder (tests/golden/ref_misst_signals.npz holds the reference's fixture files),
+trajectory files that stay inside the substrate and touch its wall, cylinder orientation
+symmetries, ellipsoid(r, r, r) == sphere(r).  Their 100-measurement protocols are one waveform
+scaled per b-value, i.e. rank 1: they run through the virtual-measurement path."""
+
+import os
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+D = 2e-9
+
+
+def example_gradient():  # test_simulations.py:460-466
+    T = 80e-3
+    gradient = np.zeros((1, 100, 3))
+    gradient[0, 1:11, 0] = 1
+    gradient[0, -11:-1, 0] = -1
+    return gradient, T / (gradient.shape[1] - 1)
+
+
+def scaled(gradient, dt, n_t, bs):
+    from disimpy_b200 import gradients
+    gradient = np.concatenate([gradient for _ in bs], axis=0)
+    gradient, dt = gradients.interpolate_gradient(gradient, dt, n_t)
+    return gradients.set_b(gradient, dt, bs), dt
+
+
+def misst_protocol(n_on, n_total, T, n_t=1000):  # test_simulations.py:527-534, 546-553
+    gradient = np.zeros((1, n_total, 3))
+    gradient[0, 1:n_on, 0] = 1
+    gradient[0, -n_on:-1, 0] = -1
+    return scaled(gradient, T / (n_total - 1), n_t, np.linspace(1, 3e9, 100))
+
+
+def trajectories(tmp_path, n_s, n_t, substrate):
+    from disimpy_b200 import gradients, simulations
+    gradient, dt = example_gradient()
+    gradient, dt = gradients.interpolate_gradient(gradient, dt, n_t)
+    path = str(tmp_path / "example_traj.txt")
+    signals = simulations.simulation(n_s, D, gradient, dt, substrate, traj=path, quiet=True)
+    tr = np.loadtxt(path)
+    assert tr.shape == (n_t + 1, n_s * 3)
+    return signals, tr.reshape((n_t + 1, n_s, 3)), gradient, dt
+
+
+def test_free_diffusion(tmp_path):  # :469-500
+    from disimpy_b200 import simulations, substrates
+    bs = np.linspace(1, 2e9, 100)
+    gradient, dt = scaled(*example_gradient(), 1000, bs)
+    signals = simulations.simulation(int(1e5), D, gradient, dt, substrates.free(), quiet=True)
+    npt.assert_almost_equal(signals / 1e5, np.exp(-bs * D), 2)
+    _, tr, _, _ = trajectories(tmp_path, int(1e4), 100, substrates.free())
+    assert np.all(tr[0] == 0)
+    npt.assert_almost_equal(np.mean(tr[-1], axis=0), 0, 5)
+
+
+@pytest.mark.parametrize("shape", ["sphere", "cylinder"])
+def test_signal_against_misst(shape):  # :521-566, :602-654
+    from disimpy_b200 import simulations, substrates
+    misst = load_golden("ref_misst_signals")
+    sub = substrates.sphere(5e-6) if shape == "sphere" else substrates.cylinder(5e-6, np.array([0, 0, 1.0]))
+    for key, (n_on, n_total, T) in {"30ms": (300, 700, 70e-3), "1ms": (10, 410, 41e-3)}.items():
+        gradient, dt = misst_protocol(n_on, n_total, T)
+        signals = simulations.simulation(int(1e5), D, gradient, dt, sub, quiet=True)
+        npt.assert_almost_equal(signals / 1e5, misst["%s_%s" % (shape, key)], 2)
+
+
+def test_cylinder_trajectories_and_orientation(tmp_path):  # :503-519, :568-584
+    from disimpy_b200 import simulations, substrates
+    for radius in [1e-6, 5e-6, 1e-3]:
+        _, tr, _, _ = trajectories(tmp_path, 100, 100, substrates.cylinder(radius, np.array([1.0, 0, 0])))
+        max_pos = np.max(np.linalg.norm(tr[..., 1::], axis=2))
+        assert max_pos < radius
+        npt.assert_almost_equal(max_pos, radius)
+    bs = np.linspace(1, 3e9, 100)
+    gradient, dt = scaled(*example_gradient(), 1000, bs)
+    n = int(1e5)
+    s1 = simulations.simulation(n, D, gradient, dt, substrates.cylinder(5e-6, np.array([1.0, 0, 1.0])), quiet=True)
+    s2 = simulations.simulation(n, D, gradient, dt, substrates.cylinder(5e-6, -np.array([1.0, 0, 1.0])), quiet=True)
+    npt.assert_almost_equal(s1 / n, s2 / n)
+    s3 = simulations.simulation(n, D, gradient, dt, substrates.cylinder(5e-6, -np.array([1.0, 0, 0])), quiet=True)
+    npt.assert_almost_equal(s3 / n, np.exp(-bs * D), 2)
+
+
+def test_sphere_and_ellipsoid_trajectories(tmp_path):  # :587-600, :657-683
+    from disimpy_b200 import simulations, substrates
+    radius = 5e-6
+    sig_sphere, tr, gradient, dt = trajectories(tmp_path, 100, 100, substrates.sphere(radius))
+    max_pos = np.max(np.linalg.norm(tr, axis=2))
+    assert max_pos < radius
+    npt.assert_almost_equal(max_pos, radius)
+    sig_ell, tr, _, _ = trajectories(tmp_path, 100, 100, substrates.ellipsoid(np.ones(3) * radius))
+    max_pos = np.max(np.linalg.norm(tr, axis=2))
+    assert max_pos < radius
+    npt.assert_almost_equal(max_pos, radius)
+    npt.assert_almost_equal(sig_ell, sig_sphere)
