@@ -102,3 +102,38 @@ def test_sphere_and_ellipsoid_trajectories(tmp_path):  # :587-600, :657-683
     assert max_pos < radius
     npt.assert_almost_equal(max_pos, radius)
     npt.assert_almost_equal(sig_ell, sig_sphere)
+
+
+def test_mesh_diffusion():  # :686-812 (the neuron model, 7.5 MB in the reference tree, is not shipped here)
+    from disimpy_b200 import simulations, substrates
+    meshes = load_golden("ref_meshes")
+    misst = load_golden("ref_misst_signals")["cylinder_30ms"]
+    gradient, dt = misst_protocol(300, 700, 70e-3)
+    n_s = int(1e4)
+    vertices, faces = meshes["cylinder_mesh_closed_vertices"], meshes["cylinder_mesh_closed_faces"]
+    for periodic in [True, False]:
+        for padding in [np.zeros(3), np.zeros(3) + 1e-6]:
+            for n_sv in [np.array([1, 1, 1]), np.array([1, 5, 20]), np.array([10, 10, 10])]:
+                substrate = substrates.mesh(vertices, faces, periodic, padding=padding, init_pos="intra",
+                                            n_sv=n_sv, quiet=True)
+                signals, pos = simulations.simulation(n_s, D, gradient, dt, substrate, final_pos=True, quiet=True)
+                npt.assert_almost_equal(signals / n_s, misst, 2)
+                # no spins leaked
+                r = np.max(np.linalg.norm(substrate.vertices[:, 0:2] - (substrate.voxel_size[0:2] - padding[0:2] * 2) / 2,
+                                          axis=1))
+                assert np.min(pos[:, 2]) > 0
+                assert np.max(pos[:, 2]) < substrate.voxel_size[2]
+                assert np.max(np.linalg.norm(pos[:, 0:2] - np.max(substrate.vertices, axis=0)[0:2] / 2, axis=1)) < r
+    # open-ended tube, periodic: walkers leave through the ends into the next voxel, never through the wall
+    vertices, faces = meshes["cylinder_mesh_open_vertices"], meshes["cylinder_mesh_open_faces"]
+    init_pos = np.zeros((n_s, 3)) + np.array([5e-6, 5e-6, 12.5e-6])
+    for padding in [np.zeros(3), np.array([1e-6, 1e-6, 0])]:
+        for n_sv in [np.array([1, 1, 1]), np.array([1, 5, 20]), np.array([10, 10, 10])]:
+            substrate = substrates.mesh(vertices, faces, init_pos=init_pos + padding, periodic=True, padding=padding,
+                                        n_sv=n_sv, quiet=True)
+            signals, pos = simulations.simulation(n_s, D, gradient, dt, substrate, final_pos=True, quiet=True)
+            r = np.max(np.linalg.norm(substrate.vertices[:, 0:2] - (substrate.voxel_size[0:2] - padding[0:2] * 2) / 2,
+                                      axis=1))
+            assert np.min(pos[:, 2]) < 0
+            assert np.max(pos[:, 2]) > substrate.voxel_size[2]
+            assert np.max(np.linalg.norm(pos[:, 0:2] - np.max(substrate.vertices, axis=0)[0:2] / 2, axis=1)) < r
