@@ -19,3 +19,6 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:walk
 export KBENCH_NT=208 KBENCH_N=400000
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:walk_kernel -s 1 -c 1 -f \
     -o gpurun_out/prof_${tag}_sphere180 python tools/kbench.py sphere180 2>&1 | tail -2
+# the same protocol on the general many-measurement path (tensor-core phase product)
+DISIMPY_B200_LOWRANK=0 timeout 300 ncu --set full --clock-control none --import-source on -k regex:walk_kernel -s 1 -c 1 -f \
+    -o gpurun_out/prof_${tag}_sphere180_general python tools/kbench.py sphere180 2>&1 | tail -2
