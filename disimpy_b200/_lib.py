@@ -68,7 +68,7 @@ EXPORTS = [
     "dsb_mesh_subdivide_fetch", "dsb_triangle_box_overlap", "dsb_interval_sv_overlap",
     "dsb_host_fill", "dsb_device_count", "dsb_last_error", "dsb_version",
     "dsb_rewind", "dsb_set_positions_part", "dsb_run_part", "dsb_finish", "dsb_release_cache",
-    "dsb_set_rng_states", "dsb_fill_mesh_sim", "dsb_protocol_rank", "dsb_set_rng_part", "dsb_host_sampler_create", "dsb_host_sampler_next", "dsb_host_sampler_destroy",
+    "dsb_set_rng_states", "dsb_fill_mesh_sim", "dsb_protocol_rank", "dsb_protocol_factor", "dsb_set_rng_part", "dsb_host_sampler_create", "dsb_host_sampler_next", "dsb_host_sampler_destroy",
 ]
 
 _lib = None
@@ -121,6 +121,8 @@ def lib():
         L.dsb_host_fill.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64,
                                     ctypes.c_void_p, ctypes.c_void_p]
         L.dsb_protocol_rank.argtypes = [ctypes.c_void_p]
+        L.dsb_protocol_factor.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
+                                          ctypes.POINTER(ctypes.c_int32), ctypes.c_void_p, ctypes.c_void_p]
         L.dsb_set_rng_part.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64]
         L.dsb_rewind.argtypes = [ctypes.c_void_p]
         L.dsb_finish.argtypes = [ctypes.c_void_p]

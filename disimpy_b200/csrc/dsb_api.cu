@@ -990,6 +990,22 @@ int dsb_measure_fp64_peak(int32_t device, double *dfma_per_second)
 }
 
 int dsb_protocol_rank(dsb_sim *s) { return s ? s->rank : 0; }
+
+int dsb_protocol_factor(const double *gradient, int64_t n_meas, int64_t n_t, int32_t max_rank, int32_t *rank, double *u,
+                        double *v)
+{
+    if (!gradient || !rank || !u || !v || n_meas <= 0 || n_t <= 0 || max_rank <= 0) return fail(DSB_EINVAL, "bad arguments");
+    std::vector<double> U, V;
+    int r = 0;
+    if (!factor_low_rank(gradient, n_meas, 3 * n_t, max_rank, U, V, r)) {
+        *rank = 0;
+        return DSB_OK;
+    }
+    *rank = r;
+    std::copy(U.begin(), U.end(), u);
+    std::copy(V.begin(), V.end(), v);
+    return DSB_OK;
+}
 void *dsb_stream(dsb_sim *s) { return s ? (void *)s->stream : nullptr; }
 double *dsb_signal_dev(dsb_sim *s) { return s ? s->d_signal : nullptr; }
 

@@ -373,3 +373,40 @@ def test_round_robin_parts_cover_all_walkers():
                 seen[a:b] += 1
                 local += b - a
         assert np.all(seen == 1)
+
+
+def test_protocol_factorisation():
+    """The rank-revealing factorisation behind the virtual-measurement path (host code): PGSE-type
+    protocols have rank <= 3 whatever the number of measurements, the factors reproduce the
+    gradient to 1e-13, near-low-rank and full-rank protocols are refused."""
+    import ctypes
+    from disimpy_b200 import _lib, gradients
+    L = _lib.lib()
+
+    def factor(g, max_rank=16):
+        g = _lib.f64(g)
+        m, t = g.shape[:2]
+        rank = ctypes.c_int32(-1)
+        u, v = np.zeros((m, max_rank)), np.zeros((max_rank, t, 3))
+        _lib.check(L.dsb_protocol_factor(_lib.ptr(g), m, t, max_rank, ctypes.byref(rank), _lib.ptr(u), _lib.ptr(v)),
+                   "dsb_protocol_factor")
+        r = rank.value
+        return r, u.ravel()[:m * r].reshape(m, r), v.ravel()[:r * t * 3].reshape(r, t, 3)
+
+    rs = np.random.RandomState(2)
+    bvecs = rs.normal(size=(180, 3))
+    g, dt = gradients.pgse(10e-3, 30e-3, 400, np.repeat([1e9, 2e9, 3e9], 60), bvecs)
+    r, u, v = factor(g)
+    assert r == 3
+    scale = np.abs(g).max()
+    assert np.abs(np.einsum("mr,rtc->mtc", u, v) - g).max() < 1e-12 * scale
+    g2, _ = gradients.pgse(5e-3, 35e-3, 400, np.repeat([1e9, 2e9, 3e9], 60), bvecs)
+    r, u, v = factor(np.concatenate([g[:90], g2[90:]]))           # two timings
+    assert r == 6 and np.abs(np.einsum("mr,rtc->mtc", u, v) - np.concatenate([g[:90], g2[90:]])).max() < 1e-12 * scale
+    assert factor(g[:1] * np.linspace(0.1, 1, 50)[:, None, None])[0] == 1   # one waveform, 50 amplitudes
+    assert factor(g + 1e-9 * scale * rs.normal(size=g.shape))[0] == 0       # noise at 1e-9: not low rank
+    assert factor(rs.normal(size=(40, 30, 3)), max_rank=16)[0] == 0         # arbitrary waveforms
+    assert factor(np.zeros((8, 10, 3)))[0] == 0                             # nothing to factor
+    bad = g.copy()
+    bad[3, 7, 1] = np.nan
+    assert factor(bad)[0] == 0                                              # non-finite samples: general path
