@@ -434,14 +434,42 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         fast &= axis_span(g.zs, g.len_zs - 1, g.vox[2], g.inv_vox[2], g.inv_hz, pos.z, ez, sz);
         n_cells = sx.count * sy.count * sz.count;
         fast = fast && n_cells <= MAXC;
+        if constexpr (MAXC == kMaxCellsShortStep) fast = fast && sx.count <= 2 && sy.count <= 2 && sz.count <= 2;
     }
-    // list ranges of this lane's cells: independent loads, all in flight together; the loops
-    // stop at the largest cell count of the warp
-    const int n_cells_warp = __reduce_max_sync(full, fast ? n_cells : 0);
+    // list ranges of this lane's cells: independent loads, all in flight together
     int2 rng[MAXC];
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) rng[c] = make_int2(0, 0);
-    {
+    // Short steps (at most 2 cells per axis): the cells are the slots of a static 2 x 2 x 2 nest,
+    // slot 4 ix + 2 iy + iz, visited in that order like the reference's x -> y -> z loops; a slot
+    // beyond an axis' count is empty.  Everything about a slot but the cell coordinates is static.
+    int off_x[2] = {0, 0}, off_y[2] = {0, 0}, off_z[2] = {0, 0};  // row offsets of the (wrapped) cells per axis
+    int wrap_x = 0, wrap_y = 0, wrap_z = 0;                        // the second cell lies in the next image
+    int n_cells_warp = 0;
+    if constexpr (MAXC == kMaxCellsShortStep) {
+        if (fast) {
+            int c1 = sx.cell + 1;
+            wrap_x = c1 >= g.len_xs - 1;
+            off_x[0] = sx.cell * g.nsv1 * g.nsv2;
+            off_x[1] = (wrap_x ? 0 : c1) * g.nsv1 * g.nsv2;
+            c1 = sy.cell + 1;
+            wrap_y = c1 >= g.len_ys - 1;
+            off_y[0] = sy.cell * g.nsv2;
+            off_y[1] = (wrap_y ? 0 : c1) * g.nsv2;
+            c1 = sz.cell + 1;
+            wrap_z = c1 >= g.len_zs - 1;
+            off_z[0] = sz.cell;
+            off_z[1] = wrap_z ? 0 : c1;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int ix = c >> 2, iy = (c >> 1) & 1, iz = c & 1;
+            if (fast && ix < sx.count && iy < sy.count && iz < sz.count)
+                rng[c] = __ldg(g.cell_rng + off_x[ix] + off_y[iy] + off_z[iz]);
+        }
+    } else {
+        // general spans: the loops stop at the largest cell count of the warp
+        n_cells_warp = __reduce_max_sync(full, fast ? n_cells : 0);
         CellWalk cw;
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
@@ -452,11 +480,11 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
             }
             cw.next(sy, sz);
         }
+    }
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-            n_ranges += rng[c].y > rng[c].x;
-            n_entries += rng[c].y - rng[c].x;
-        }
+    for (int c = 0; c < MAXC; ++c) {
+        n_ranges += rng[c].y > rng[c].x;
+        n_entries += rng[c].y - rng[c].x;
     }
     // this lane's place in the warp's numbering of ranges and entries
     int incl_r = n_ranges, incl_e = n_entries;
@@ -495,14 +523,9 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         const unsigned hy[2] = {clamp15(hiy), clamp15(hiy - 32767)}, ly[2] = {32767u - clamp15(loy), 32767u - clamp15(loy - 32767)};
         const unsigned hz[2] = {clamp15(hiz), clamp15(hiz - 32767)}, lz[2] = {32767u - clamp15(loz), 32767u - clamp15(loz - 32767)};
         int k = incl_r - n_ranges, first = incl_e - n_entries;
-        CellWalk cw;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-            if (c >= n_cells_warp) break;
+        auto add_range = [&](int c, int flags) {
             const int n = rng[c].y - rng[c].x;
             if (n > 0) {
-                int flags;
-                cw.index(g, sx, sy, sz, flags);
                 const int fx = flags & 1, fy = (flags >> 1) & 1, fz = flags >> 2;
                 // triangle box (lo, 32767 - hi) <= these, halfword by halfword  <=>  the boxes meet
                 sc.range_box[k] = make_uint4(((fx ? hx[1] : hx[0]) | ((fy ? hy[1] : hy[0]) << 16)) + kSwarH,
@@ -515,7 +538,21 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
                 ++k;
                 first += n;
             }
-            cw.next(sy, sz);
+        };
+        if constexpr (MAXC == kMaxCellsShortStep) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                add_range(c, ((c >> 2) & wrap_x) | ((((c >> 1) & 1) & wrap_y) << 1) | (((c & 1) & wrap_z) << 2));
+        } else {
+            CellWalk cw;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) {
+                if (c >= n_cells_warp) break;
+                int flags;
+                cw.index(g, sx, sy, sz, flags);
+                add_range(c, flags);
+                cw.next(sy, sz);
+            }
         }
     }
     __syncwarp();
