@@ -209,6 +209,7 @@ cudaError_t cache_malloc(T **out, size_t bytes)
 
 struct MeshBuffers {
     double *tri = nullptr;
+    double *normal = nullptr;
     int *tri_idx = nullptr;
     uint4 *entry = nullptr;
     int2 *cell_rng = nullptr;
@@ -217,6 +218,7 @@ struct MeshBuffers {
     void release()
     {
         cache_free(tri);
+        cache_free(normal);
         cache_free(tri_idx);
         cache_free(entry);
         cache_free(cell_rng);
@@ -298,6 +300,10 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
     DSB_CUDA(cache_malloc(&mb.ys, (m.n_sv[1] + 1) * sizeof(double)));
     DSB_CUDA(cache_malloc(&mb.zs, (m.n_sv[2] + 1) * sizeof(double)));
     DSB_CUDA(cudaMemcpy(mb.tri, tri.data(), tri.size() * sizeof(double), cudaMemcpyHostToDevice));
+    DSB_CUDA(cache_malloc(&mb.normal, sizeof(double) * 3 * (size_t)m.n_faces));
+    dsb::tri_normal_kernel<<<(unsigned)((m.n_faces + 255) / 256), 256>>>(mb.tri, (long long)m.n_faces, mb.normal);
+    DSB_CUDA(cudaGetLastError());
+    DSB_CUDA(cudaDeviceSynchronize());
     if (!tri_idx.empty())
         DSB_CUDA(cudaMemcpy(mb.tri_idx, tri_idx.data(), tri_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaMemcpy(mb.cell_rng, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -306,6 +312,7 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
     DSB_CUDA(cudaMemcpy(mb.zs, m.zs, (m.n_sv[2] + 1) * sizeof(double), cudaMemcpyHostToDevice));
     dsb::MeshDev &d = mb.dev;
     d.tri = mb.tri;
+    d.normal = mb.normal;
     d.tri_idx = mb.tri_idx;
     d.entry = mb.entry;
     d.cell_rng = mb.cell_rng;

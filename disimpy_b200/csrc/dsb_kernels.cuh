@@ -40,6 +40,7 @@ constexpr int kGradRows = DSB_GRADROWS;  // measurements per gradient tile stage
 struct MeshDev {
     const double *tri;      // (n_faces, kTriStride): A, B-A, C-A, pad
     const int *tri_idx;     // (K,) triangle ids, cell after cell (reference order)
+    const double *normal;   // (n_faces, 3) unit normals, computed once with the walk's own arithmetic (tri_normal_kernel)
     const uint4 *entry;     // (K,) per list entry: triangle id, box (lo, 32767 - hi) on a 15-bit grid, 3 x 2 halfwords
     const int2 *cell_rng;   // (n_cells,) [begin, end) into tri_idx
     const double *xs, *ys, *zs;
@@ -642,13 +643,28 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
     }
 }
 
+// unit normal of every triangle, once per mesh upload (same device functions the reference's
+// per-collision computation is restated with: _cuda_triangle_normal, simulations.py:77-97)
+__global__ void __launch_bounds__(256) tri_normal_kernel(const double *tri, long long n_faces, double *normal)
+{
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_faces) return;
+    const Vec3 n = triangle_normal(load_tri(tri, (int)f));
+    normal[3 * f] = n.x;
+    normal[3 * f + 1] = n.y;
+    normal[3 * f + 2] = n.z;
+}
+
 // What happens at the closest triangle (simulations.py:986-997): one uniform draw (also when
 // perm_prob == 0), then reflection or passage through the membrane.
 __device__ __forceinline__ void mesh_collision(const MeshDev &g, Vec3 &pos, Vec3 &s, Rng &rng, double min_d,
                                                int closest, double eps)
 {
     const double u = u01_f64(rng_next(rng));
-    const Vec3 n = triangle_normal(load_tri(g.tri, closest));
+    // the reference recomputes the normal at every collision (simulations.py:77-97); it only depends
+    // on the triangle, so it is read from the table tri_normal_kernel filled with the same arithmetic
+    const double *nq = g.normal + 3ll * closest;
+    const Vec3 n = {__ldg(nq), __ldg(nq + 1), __ldg(nq + 2)};
     if (g.perm_prob < u)
         reflect(pos, s, min_d, n, eps);
     else
