@@ -215,8 +215,19 @@ struct MeshBuffers {
     int2 *cell_rng = nullptr;
     double *xs = nullptr, *ys = nullptr, *zs = nullptr;
     dsb::MeshDev dev{};
+    // host copies the initial-position sampler's column lists are built from on first use
+    std::vector<int2> h_cells;
+    std::vector<int> h_tri_idx;
+    std::vector<uint4> h_box;
+    int64_t n_sv[3] = {0, 0, 0};
+    int *col_start = nullptr, *col_cnt = nullptr;
+    uint4 *col_entry = nullptr;
+    dsb::FillColumns columns{};
     void release()
     {
+        cache_free(col_start);
+        cache_free(col_cnt);
+        cache_free(col_entry);
         cache_free(tri);
         cache_free(normal);
         cache_free(tri_idx);
@@ -275,7 +286,15 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
             lo[k] = (unsigned)std::min(ql, 32767.0);
             hi[k] = 32767u - (unsigned)std::max(qh, 0.0);
         }
-        box[(size_t)f] = make_uint4((unsigned)f, lo[0] | (lo[1] << 16), lo[2] | (hi[0] << 16), hi[1] | (hi[2] << 16));
+        // Seen along +x (the sampler's ray, dsb_fill.cuh) a triangle whose projection on the yz plane is
+        // a sliver has a determinant that is mostly rounding error, and the reference's test may then
+        // accept points far outside its box: such triangles are marked and always tested exactly.
+        const double *o = &tri[(size_t)f * dsb::kTriStride];
+        const double det = std::fma(o[7], o[5], -(o[8] * o[4]));  // as ray_triangle forms it for ray = (1,0,0)
+        const double scale_yz = std::hypot(o[4], o[5]) * std::hypot(o[7], o[8]);
+        const bool edge_on = det != 0.0 && !(std::fabs(det) > 1e-9 * scale_yz);
+        box[(size_t)f] = make_uint4((unsigned)f | (edge_on ? ~dsb::kEntryTriMask : 0u), lo[0] | (lo[1] << 16),
+                                    lo[2] | (hi[0] << 16), hi[1] | (hi[2] << 16));
     }
     std::vector<int> tri_idx((size_t)m.n_triangle_indices);
     std::vector<uint4> entry((size_t)m.n_triangle_indices + 1);
@@ -335,6 +354,52 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
         d.qscale[k] = 32767.0 / d.top[k];
     }
     d.perm_prob = m.perm_prob;
+    mb.h_cells = std::move(cells);
+    mb.h_tri_idx = std::move(tri_idx);
+    mb.h_box = std::move(box);
+    for (int k = 0; k < 3; ++k) mb.n_sv[k] = m.n_sv[k];
+    return DSB_OK;
+}
+
+// Column lists for the sampler's +x rays (dsb::FillColumns): per (y, z) column the distinct
+// triangles of its cells, those of the last x cell first.  One pass over the cell lists.
+int build_fill_columns(MeshBuffers &mb)
+{
+    if (mb.columns.entry) return DSB_OK;
+    const int64_t n0 = mb.n_sv[0], n1 = mb.n_sv[1], n2 = mb.n_sv[2];
+    const int64_t n_cols = n1 * n2;
+    std::vector<int> start((size_t)n_cols + 1), cnt((size_t)(n_cols * n0));
+    std::vector<uint4> entry;
+    entry.reserve(mb.h_tri_idx.size());
+    std::vector<int64_t> seen_in(mb.h_box.size(), -1);
+    for (int64_t col = 0; col < n_cols; ++col) {
+        const int64_t y = col / n2, z = col % n2;
+        const size_t begin = entry.size();
+        start[(size_t)col] = (int)begin;
+        for (int64_t x = n0 - 1; x >= 0; --x) {
+            const int2 c = mb.h_cells[(size_t)((x * n1 + y) * n2 + z)];
+            for (int i = c.x; i < c.y; ++i) {
+                const int t = mb.h_tri_idx[(size_t)i];
+                if (seen_in[(size_t)t] != col) {
+                    seen_in[(size_t)t] = col;
+                    entry.push_back(mb.h_box[(size_t)t]);
+                }
+            }
+            cnt[(size_t)(col * n0 + x)] = (int)(entry.size() - begin);
+        }
+    }
+    start[(size_t)n_cols] = (int)entry.size();
+    entry.push_back(make_uint4(0u, 0xffffffffu, 0xffffffffu, 0xffffffffu));
+    DSB_CUDA(cache_malloc(&mb.col_start, start.size() * sizeof(int)));
+    DSB_CUDA(cache_malloc(&mb.col_cnt, cnt.size() * sizeof(int)));
+    DSB_CUDA(cache_malloc(&mb.col_entry, entry.size() * sizeof(uint4)));
+    DSB_CUDA(cudaMemcpy(mb.col_start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaMemcpy(mb.col_cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaMemcpy(mb.col_entry, entry.data(), entry.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    mb.columns.start = mb.col_start;
+    mb.columns.cnt = mb.col_cnt;
+    mb.columns.entry = mb.col_entry;
+    mb.columns.n0 = (int)n0;
     return DSB_OK;
 }
 
@@ -1068,6 +1133,7 @@ int dsb_fill_mesh_sim(dsb_sim *s, const double *voxel_size, int intra, uint64_t 
     if (e == cudaSuccess) e = cache_malloc(&d_pts, sizeof(double) * 3 * (size_t)n_points);
     if (e == cudaSuccess) e = cache_malloc(&d_totals, sizeof(int) * (size_t)(n_blocks + 1));
     int rc = e == cudaSuccess ? DSB_OK : fail(DSB_ENOMEM, cudaGetErrorString(e));
+    if (!rc) rc = build_fill_columns(s->mesh);
     if (!rc) rc = launch_rng_init(s->prm.device, seed, 0, n_states, d_rng, s->stream);
     int64_t have = 0;
     // one round per iteration like the reference's host loop (simulations.py:554-579): every
@@ -1078,7 +1144,7 @@ int dsb_fill_mesh_sim(dsb_sim *s, const double *voxel_size, int intra, uint64_t 
             break;
         }
         dsb::fill_mesh_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, s->stream>>>(
-            s->mesh.dev, voxel_size[0], voxel_size[1], voxel_size[2], intra, (long long)n_points, d_rng, d_pts);
+            s->mesh.dev, s->mesh.columns, voxel_size[0], voxel_size[1], voxel_size[2], intra, (long long)n_points, d_rng, d_pts);
         dsb::fill_count_kernel<<<n_blocks, dsb::kCompactBlock, 0, s->stream>>>(d_pts, (long long)n_points, d_totals);
         dsb::fill_scan_kernel<<<1, 1024, 0, s->stream>>>(d_totals, n_blocks);
         dsb::fill_scatter_kernel<<<n_blocks, dsb::kCompactBlock, 0, s->stream>>>(
@@ -1119,6 +1185,7 @@ int dsb_fill_mesh(int32_t device, const dsb_mesh *mesh, const double *voxel_size
     if (e == cudaSuccess) e = cudaMalloc(&d_pts, sizeof(double) * 3 * (size_t)n_points);
     if (e == cudaSuccess) e = cudaMalloc(&d_count, sizeof(int));
     if (e != cudaSuccess) rc = fail(DSB_ENOMEM, cudaGetErrorString(e));
+    if (!rc) rc = build_fill_columns(mb);
     if (!rc) rc = launch_rng_init(device, seed, 0, n_states, d_rng, 0);
     std::vector<double> round_pts((size_t)n_points * 3);
     int64_t have = 0;
@@ -1130,7 +1197,7 @@ int dsb_fill_mesh(int32_t device, const dsb_mesh *mesh, const double *voxel_size
             rc = fail(DSB_ESTATE, "fill_mesh: no acceptable points (is the surface closed?)");
             break;
         }
-        dsb::fill_mesh_kernel<<<(unsigned)((n_points + 127) / 128), 128>>>(mb.dev, voxel_size[0], voxel_size[1],
+        dsb::fill_mesh_kernel<<<(unsigned)((n_points + 127) / 128), 128>>>(mb.dev, mb.columns, voxel_size[0], voxel_size[1],
                                                                             voxel_size[2], intra, (long long)n_points,
                                                                             d_rng, d_pts);
         e = cudaGetLastError();

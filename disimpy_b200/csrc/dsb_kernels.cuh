@@ -305,6 +305,9 @@ constexpr int kSurvivorCap = 256;  // triangles per warp and search that pass th
 constexpr int kRangeCap = 128;     // non-empty cell lists per warp and search
 constexpr int kEntryCap = 4096;    // list entries per warp and search
 constexpr unsigned kSwarH = 0x80008000u;
+// bit 31 of a list entry's triangle word: the triangle is (nearly) edge-on to the +x axis, the
+// initial-position sampler must not trust its box (dsb_fill.cuh)
+constexpr unsigned kEntryTriMask = 0x7fffffffu;
 
 // Per-warp scratch of the collision search.
 struct MeshScratch {
@@ -608,7 +611,7 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         o.y = sc.org[1][(flags >> 1) & 1][owner];
         o.z = sc.org[2][(flags >> 2) & 1][owner];
         dir.x = sc.dir[0][owner]; dir.y = sc.dir[1][owner]; dir.z = sc.dir[2][owner];
-        const double t = ray_triangle(load_tri(g.tri, (int)(unsigned)w), o, dir);
+        const double t = ray_triangle(load_tri(g.tri, (int)((unsigned)w & kEntryTriMask)), o, dir);
         const bool is_hit = t > 0;
         sc.hit[j] = is_hit ? t : inf;
         if (is_hit) atomicMin(&sc.best_d[owner], (unsigned long long)__double_as_longlong(t));
@@ -628,7 +631,7 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         const double t = sc.hit[j];
         if (t < inf && (unsigned long long)__double_as_longlong(t) == sc.best_d[hi & 0xff] &&
             (hi >> 16) == sc.best_key[hi & 0xff])
-            sc.best_tri[hi & 0xff] = (int)(unsigned)w;
+            sc.best_tri[hi & 0xff] = (int)((unsigned)w & kEntryTriMask);
     }
     __syncwarp();
 
