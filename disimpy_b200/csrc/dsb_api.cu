@@ -132,7 +132,7 @@ int launch_rng_init(int device, uint64_t seed, uint64_t start, int64_t n, ulongl
     ulonglong2 *pows = nullptr;
     int rc = device_jump_powers(device, &pows);
     if (rc) return rc;
-    int64_t blocks = (n + 255) / 256;
+    int64_t blocks = (n + 256 * dsb::kRngInitRun - 1) / (256 * dsb::kRngInitRun);
     dsb::rng_init_kernel<<<(unsigned)blocks, 256, 0, st>>>(splitmix64(seed), start, (long long)n, pows, d_out);
     DSB_CUDA(cudaGetLastError());
     return DSB_OK;
@@ -1135,29 +1135,46 @@ int dsb_fill_mesh_sim(dsb_sim *s, const double *voxel_size, int intra, uint64_t 
     int rc = e == cudaSuccess ? DSB_OK : fail(DSB_ENOMEM, cudaGetErrorString(e));
     if (!rc) rc = build_fill_columns(s->mesh);
     if (!rc) rc = launch_rng_init(s->prm.device, seed, 0, n_states, d_rng, s->stream);
-    int64_t have = 0;
-    // one round per iteration like the reference's host loop (simulations.py:554-579): every
-    // thread proposes a point, the accepted ones are appended in thread order
+    int64_t have = 0, proposed = 0;
+    // One round per iteration like the reference's host loop (simulations.py:554-579): every thread
+    // proposes a point, the accepted ones are appended in thread order until there are n_points.
+    // Only the threads up to the one that supplies the last point matter, so from the second round
+    // on a round is run as a prefix sized from the acceptance rate so far, and continued in thread
+    // order if that was not enough.
     for (int round = 0; !rc && have < n_points; ++round) {
         if (round > 100000) {
             rc = fail(DSB_ESTATE, "fill_mesh: no acceptable points (is the surface closed?)");
             break;
         }
-        dsb::fill_mesh_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, s->stream>>>(
-            s->mesh.dev, s->mesh.columns, voxel_size[0], voxel_size[1], voxel_size[2], intra, (long long)n_points, d_rng, d_pts);
-        dsb::fill_count_kernel<<<n_blocks, dsb::kCompactBlock, 0, s->stream>>>(d_pts, (long long)n_points, d_totals);
-        dsb::fill_scan_kernel<<<1, 1024, 0, s->stream>>>(d_totals, n_blocks);
-        dsb::fill_scatter_kernel<<<n_blocks, dsb::kCompactBlock, 0, s->stream>>>(
-            d_pts, (long long)n_points, d_totals, (long long)have, (long long)first, (long long)s->prm.n_walkers, s->d_pos);
-        int accepted = 0;
-        e = cudaMemcpyAsync(&accepted, d_totals + n_blocks, sizeof(int), cudaMemcpyDeviceToHost, s->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-        if (e == cudaSuccess) e = cudaGetLastError();
-        if (e != cudaSuccess) {
-            rc = fail(DSB_ECUDA, cudaGetErrorString(e));
-            break;
+        for (int64_t c0 = 0; !rc && c0 < n_points && have < n_points;) {
+            int64_t want = n_points - c0;
+            if (have > 0) {
+                const double rate = (double)have / (double)proposed;
+                const double need = (double)(n_points - have) / rate * 1.02 + 8192.0;
+                if (need < (double)want) want = ((int64_t)need + dsb::kCompactBlock - 1) / dsb::kCompactBlock * dsb::kCompactBlock;
+                want = std::min(want, n_points - c0);
+            }
+            const int chunk_blocks = (int)((want + dsb::kCompactBlock - 1) / dsb::kCompactBlock);
+            double *pts = d_pts + 3 * c0;
+            dsb::fill_mesh_kernel<<<(unsigned)((want + 127) / 128), 128, 0, s->stream>>>(
+                s->mesh.dev, s->mesh.columns, voxel_size[0], voxel_size[1], voxel_size[2], intra, (long long)want,
+                d_rng + c0, pts);
+            dsb::fill_count_kernel<<<chunk_blocks, dsb::kCompactBlock, 0, s->stream>>>(pts, (long long)want, d_totals);
+            dsb::fill_scan_kernel<<<1, 1024, 0, s->stream>>>(d_totals, chunk_blocks);
+            dsb::fill_scatter_kernel<<<chunk_blocks, dsb::kCompactBlock, 0, s->stream>>>(
+                pts, (long long)want, d_totals, (long long)have, (long long)first, (long long)s->prm.n_walkers, s->d_pos);
+            int accepted = 0;
+            e = cudaMemcpyAsync(&accepted, d_totals + chunk_blocks, sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e != cudaSuccess) {
+                rc = fail(DSB_ECUDA, cudaGetErrorString(e));
+                break;
+            }
+            have += accepted;
+            proposed += want;
+            c0 += want;
         }
-        have += accepted;
     }
     cache_free(d_rng);
     cache_free(d_pts);

@@ -1200,37 +1200,47 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 // state[i] = J^(start + i) * splitmix64(seed), J = the 2^64-step jump of xoroshiro128+ as a
 // 128x128 matrix over GF(2).  pows[k] holds J^(2^k) column by column (column b = image of unit
 // vector b); applying the matrices for the set bits of the index reproduces numba's sequential
-// jump chain (numba/cuda/random.py:102-126, 225-241) without the O(N) host loop.
+// jump chain (numba/cuda/random.py:102-126, 225-241) without the O(N) host loop.  A thread
+// derives kRngInitRun consecutive states: the first from the bits of its index, the others by one
+// more application of J each.
+constexpr int kRngInitRun = 8;
+
+__device__ __forceinline__ void gf2_apply(const ulonglong2 *col, unsigned long long &s0, unsigned long long &s1)
+{
+    unsigned long long a0 = 0, a1 = 0;
+#pragma unroll 8
+    for (int b = 0; b < 64; ++b) {
+        ulonglong2 c = __ldg(col + b);
+        unsigned long long mask = 0ull - ((s0 >> b) & 1ull);
+        a0 ^= c.x & mask;
+        a1 ^= c.y & mask;
+    }
+#pragma unroll 8
+    for (int b = 0; b < 64; ++b) {
+        ulonglong2 c = __ldg(col + 64 + b);
+        unsigned long long mask = 0ull - ((s1 >> b) & 1ull);
+        a0 ^= c.x & mask;
+        a1 ^= c.y & mask;
+    }
+    s0 = a0;
+    s1 = a1;
+}
+
 __global__ void __launch_bounds__(256) rng_init_kernel(unsigned long long z, unsigned long long start,
                                                        long long n, const ulonglong2 *pows,
                                                        ulonglong2 *out)
 {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kRngInitRun;
     if (i >= n) return;
-    unsigned long long idx = start + (unsigned long long)i;
+    const unsigned long long idx = start + (unsigned long long)i;
     unsigned long long s0 = z, s1 = z;
-    for (int k = 0; k < 64 && (idx >> k) != 0; ++k) {
-        if (((idx >> k) & 1ull) == 0) continue;
-        const ulonglong2 *col = pows + 128 * k;
-        unsigned long long a0 = 0, a1 = 0;
-#pragma unroll 8
-        for (int b = 0; b < 64; ++b) {
-            ulonglong2 c = __ldg(col + b);
-            unsigned long long mask = 0ull - ((s0 >> b) & 1ull);
-            a0 ^= c.x & mask;
-            a1 ^= c.y & mask;
-        }
-#pragma unroll 8
-        for (int b = 0; b < 64; ++b) {
-            ulonglong2 c = __ldg(col + 64 + b);
-            unsigned long long mask = 0ull - ((s1 >> b) & 1ull);
-            a0 ^= c.x & mask;
-            a1 ^= c.y & mask;
-        }
-        s0 = a0;
-        s1 = a1;
-    }
+    for (int k = 0; k < 64 && (idx >> k) != 0; ++k)
+        if ((idx >> k) & 1ull) gf2_apply(pows + 128 * k, s0, s1);
     out[i] = make_ulonglong2(s0, s1);
+    for (int j = 1; j < kRngInitRun && i + j < n; ++j) {
+        gf2_apply(pows, s0, s1);
+        out[i + j] = make_ulonglong2(s0, s1);
+    }
 }
 
 }  // namespace dsb
