@@ -69,6 +69,7 @@ EXPORTS = [
     "dsb_host_fill", "dsb_device_count", "dsb_last_error", "dsb_version",
     "dsb_rewind", "dsb_set_positions_part", "dsb_run_part", "dsb_finish", "dsb_release_cache",
     "dsb_set_rng_states", "dsb_fill_mesh_sim", "dsb_protocol_rank", "dsb_protocol_factor", "dsb_set_rng_part", "dsb_host_sampler_create", "dsb_host_sampler_next", "dsb_host_sampler_destroy",
+    "dsb_fill_shard_begin", "dsb_fill_shard_round", "dsb_fill_shard_end",
 ]
 
 _lib = None
@@ -131,6 +132,9 @@ def lib():
         L.dsb_set_rng_states.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.dsb_fill_mesh_sim.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64,
                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_int64]
+        L.dsb_fill_shard_begin.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64]
+        L.dsb_fill_shard_round.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, c_int64_p]
+        L.dsb_fill_shard_end.argtypes = [ctypes.c_void_p]
         L.dsb_host_sampler_create.argtypes = [ctypes.c_int32, ctypes.c_uint64, ctypes.c_void_p,
                                               ctypes.POINTER(ctypes.c_void_p)]
         L.dsb_host_sampler_next.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]

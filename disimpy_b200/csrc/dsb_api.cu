@@ -413,6 +413,11 @@ struct dsb_sim {
     cudaStream_t stream2 = nullptr;  // every other part of a part-by-part run (dsb_run_part)
     cudaEvent_t ev_rewind = nullptr, ev_parts = nullptr;
     int part_parity = 0;
+    // sampler threads [fill_t0, fill_t1) of a multi-rank run (dsb_fill_shard_*)
+    ulonglong2 *fill_rng = nullptr;
+    double *fill_pts = nullptr;
+    int *fill_totals = nullptr;
+    int64_t fill_t0 = 0, fill_t1 = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double *d_grad = nullptr, *d_grad_chunked = nullptr, *d_pos = nullptr, *d_phases = nullptr, *d_partials = nullptr, *d_signal = nullptr;
     unsigned long long *d_rng = nullptr, *d_rng0 = nullptr;
@@ -642,6 +647,9 @@ int dsb_destroy(dsb_sim *s)
     cache_free(s->d_rng);
     cache_free(s->d_rng0);
     cache_free(s->d_exc);
+    cache_free(s->fill_rng);
+    cache_free(s->fill_pts);
+    cache_free(s->fill_totals);
     s->mesh.release();
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->stream2) cudaStreamDestroy(s->stream2);
@@ -1181,6 +1189,67 @@ int dsb_fill_mesh_sim(dsb_sim *s, const double *voxel_size, int intra, uint64_t 
     cache_free(d_totals);
     if (rc) return rc;
     return rewind_sim(s);
+}
+
+int dsb_fill_shard_end(dsb_sim *s)
+{
+    if (!s) return fail(DSB_EINVAL, "null argument");
+    cudaSetDevice(s->prm.device);
+    cache_free(s->fill_rng);
+    cache_free(s->fill_pts);
+    cache_free(s->fill_totals);
+    s->fill_rng = nullptr;
+    s->fill_pts = nullptr;
+    s->fill_totals = nullptr;
+    s->fill_t0 = s->fill_t1 = 0;
+    return DSB_OK;
+}
+
+int dsb_fill_shard_begin(dsb_sim *s, uint64_t seed, int64_t thread_begin, int64_t thread_end)
+{
+    if (!s || thread_begin < 0 || thread_end <= thread_begin || thread_end > 0x7fffffffLL)
+        return fail(DSB_EINVAL, "bad arguments");
+    if (s->prm.substrate != DSB_MESH) return fail(DSB_ESTATE, "dsb_fill_shard_begin needs a mesh handle");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    dsb_fill_shard_end(s);
+    const int64_t n = thread_end - thread_begin;
+    const int n_blocks = (int)((n + dsb::kCompactBlock - 1) / dsb::kCompactBlock);
+    cudaError_t e = cache_malloc(&s->fill_rng, sizeof(ulonglong2) * (size_t)n);
+    if (e == cudaSuccess) e = cache_malloc(&s->fill_pts, sizeof(double) * 3 * (size_t)n);
+    if (e == cudaSuccess) e = cache_malloc(&s->fill_totals, sizeof(int) * (size_t)(n_blocks + 1));
+    int rc = e == cudaSuccess ? DSB_OK : fail(DSB_ENOMEM, cudaGetErrorString(e));
+    if (!rc) rc = build_fill_columns(s->mesh);
+    if (!rc) rc = launch_rng_init(s->prm.device, seed, (uint64_t)thread_begin, n, s->fill_rng, s->stream);
+    if (rc) {
+        std::string keep = g_err;
+        dsb_fill_shard_end(s);
+        return fail(rc, keep);
+    }
+    s->fill_t0 = thread_begin;
+    s->fill_t1 = thread_end;
+    return DSB_OK;
+}
+
+int dsb_fill_shard_round(dsb_sim *s, const double *voxel_size, int intra, double *accepted_dev, int64_t *n_accepted)
+{
+    if (!s || !voxel_size || !accepted_dev || !n_accepted) return fail(DSB_EINVAL, "null argument");
+    if (!s->fill_rng) return fail(DSB_ESTATE, "dsb_fill_shard_round before dsb_fill_shard_begin");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    const int64_t n = s->fill_t1 - s->fill_t0;
+    const int n_blocks = (int)((n + dsb::kCompactBlock - 1) / dsb::kCompactBlock);
+    dsb::fill_mesh_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(
+        s->mesh.dev, s->mesh.columns, voxel_size[0], voxel_size[1], voxel_size[2], intra, (long long)n, s->fill_rng,
+        s->fill_pts);
+    dsb::fill_count_kernel<<<n_blocks, dsb::kCompactBlock, 0, s->stream>>>(s->fill_pts, (long long)n, s->fill_totals);
+    dsb::fill_scan_kernel<<<1, 1024, 0, s->stream>>>(s->fill_totals, n_blocks);
+    dsb::fill_scatter_kernel<<<n_blocks, dsb::kCompactBlock, 0, s->stream>>>(s->fill_pts, (long long)n, s->fill_totals, 0LL,
+                                                                            0LL, (long long)n, accepted_dev);
+    int accepted = 0;
+    DSB_CUDA(cudaMemcpyAsync(&accepted, s->fill_totals + n_blocks, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    DSB_CUDA(cudaStreamSynchronize(s->stream));
+    DSB_CUDA(cudaGetLastError());
+    *n_accepted = accepted;
+    return DSB_OK;
 }
 
 int dsb_fill_mesh(int32_t device, const dsb_mesh *mesh, const double *voxel_size, int intra, uint64_t seed,

@@ -311,6 +311,22 @@ class Walk:
         _lib.check(self._L.dsb_fill_mesh_sim(self._h, _lib.ptr(voxel), 1 if intra else 0, seed, n_points, first,
                                              cuda_bs), "dsb_fill_mesh_sim")
 
+    def fill_shard_begin(self, seed, thread_begin, thread_end):
+        _lib.check(self._L.dsb_fill_shard_begin(self._h, seed, thread_begin, thread_end), "dsb_fill_shard_begin")
+
+    def fill_shard_round(self, voxel_size, intra, accepted_dev_ptr):
+        """One round of the sampler for this handle's threads; returns how many points were
+        accepted (written to device memory at ``accepted_dev_ptr``, thread order)."""
+        voxel = _lib.f64(voxel_size)
+        n = ctypes.c_int64(0)
+        _lib.check(self._L.dsb_fill_shard_round(self._h, _lib.ptr(voxel), 1 if intra else 0,
+                                                ctypes.c_void_p(accepted_dev_ptr), ctypes.byref(n)),
+                   "dsb_fill_shard_round")
+        return n.value
+
+    def fill_shard_end(self):
+        _lib.check(self._L.dsb_fill_shard_end(self._h), "dsb_fill_shard_end")
+
     def protocol_rank(self):
         """r > 0: the protocol's gradient matrix has rank r <= 4 and the walk carries r virtual
         measurements (see include/disimpy_b200.h); 0: general path."""
@@ -481,7 +497,10 @@ def simulation(
         if pipelined:
             _walk_pipelined(walk, substrate, owned, seed)
         elif device_fill:
-            walk.fill_mesh(substrate.voxel_size, substrate.init_pos == "intra", seed, n_walkers, lo, cuda_bs)
+            if world > 1 and dist.get_backend() == "nccl" and n_walkers >= _SHARDED_FILL_MIN:
+                _fill_mesh_sharded(walk, substrate, n_walkers, lo, n_local, seed, rank, world, dist)
+            else:
+                walk.fill_mesh(substrate.voxel_size, substrate.init_pos == "intra", seed, n_walkers, lo, cuda_bs)
             if traj:
                 start = _gather_rows(walk.positions(), n_walkers, owned, dist)
                 if rank == 0:
@@ -602,6 +621,50 @@ def _walk_pipelined(walk, substrate, owned, seed):
             walk.set_positions_part(la, la + b - a, pts)
             walk.run_part(la, la + b - a)
     walk.finish()
+
+
+# from this many walkers on, the ranks of a multi-GPU run share the work of the mesh sampler
+_SHARDED_FILL_MIN = 1 << 20
+
+
+def _fill_mesh_sharded(walk, substrate, n_points, lo, n_local, seed, rank, world, dist):
+    """The reference's mesh sampler (disimpy/simulations.py:505-579) with its threads dealt to the
+    ranks: in every round rank r evaluates threads shard_range(n_points, r, world), the accepted
+    points of all ranks are all-gathered (NCCL) and concatenated in rank = thread order, and each
+    rank keeps the rows [lo, lo + n_local) of the first n_points.  Same points, same order as one
+    GPU drawing everything; 1/world of the ray tests per rank."""
+    import torch
+    dev = torch.device("cuda", _device())
+    intra = substrate.init_pos == "intra"
+    t0, t1 = shard_range(n_points, rank, world)
+    cap = max(b - a for a, b in (shard_range(n_points, r, world) for r in range(world)))
+    mine = torch.empty((n_local, 3), dtype=torch.float64, device=dev)
+    accepted = torch.empty((cap, 3), dtype=torch.float64, device=dev)
+    everyone = torch.empty((world, cap, 3), dtype=torch.float64, device=dev)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    walk.fill_shard_begin(seed, t0, t1)
+    try:
+        have = 0
+        for _ in range(100000):
+            n_acc = walk.fill_shard_round(substrate.voxel_size, intra, accepted.data_ptr())
+            dist.all_gather_into_tensor(counts, torch.tensor([n_acc], dtype=torch.int64, device=dev))
+            dist.all_gather_into_tensor(everyone, accepted)
+            start = have
+            for r, c in enumerate(counts.tolist()):
+                a, b = max(start, lo), min(start + c, lo + n_local)
+                if a < b:
+                    mine[a - lo:b - lo] = everyone[r, a - start:b - start]
+                start += c
+            have = start
+            if have >= n_points:
+                break
+        else:
+            raise RuntimeError("fill_mesh: no acceptable points (is the surface closed?)")
+    finally:
+        walk.fill_shard_end()
+    torch.cuda.synchronize(dev)
+    walk.set_positions_dev(mine.data_ptr())
+    walk.sync()
 
 
 def _allreduce_sum(values, dist):

@@ -29,6 +29,9 @@ cases = [("sphere 600k (round-robin parts)", 600_000, g1, dt1, substrates.sphere
          ("sphere 1000 (contiguous shards)", 1000, g1, dt1, substrates.sphere(5e-6)),
          ("ellipsoid 400k, 12 measurements", 400_000, g12, dt12, substrates.ellipsoid(np.array([5e-6, 3e-6, 2e-6]))),
          ("periodic mesh 50k, init_pos extra", 50_000, g1, dt1, mesh)]
+simulations._SHARDED_FILL_MIN = 0     # the mesh sampler's threads are dealt to the ranks even for this small run
+mesh_intra = substrates.mesh(v, f, True, padding=pad, init_pos="intra", n_sv=np.array([8, 8, 6]), quiet=True)
+cases.append(("periodic mesh 30001, init_pos intra", 30_001, g1, dt1, mesh_intra))
 real_dist = simulations._dist
 for name, n, g, dt, sub in cases:
     t0 = time.time()
