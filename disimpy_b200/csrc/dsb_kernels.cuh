@@ -811,6 +811,9 @@ __device__ __forceinline__ bool time_step(Vec3 &pos, Rng &rng, const KParams &p,
 #ifndef DSB_PARK
 #define DSB_PARK 1
 #endif
+#ifndef DSB_MESH_SMEM_PHASES_FROM
+#define DSB_MESH_SMEM_PHASES_FROM 2   // measurements from which the mesh walk keeps its phases in shared memory
+#endif
 #ifndef DSB_PARK_ELLIPSOID
 #define DSB_PARK_ELLIPSOID 6
 #endif
@@ -857,13 +860,25 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
         double ph[MR];
 #pragma unroll
         for (int m = 0; m < MR; ++m) ph[m] = (active && p.t0 > 0) ? p.phases[(long long)m * N + w] : 0.0;
+        // The mesh search runs at the register cap: with more than one measurement the phases
+        // live in shared memory during the walk (the registers they would hold cost the search
+        // loop its load pipelining: -15 % at 3 measurements).
+        constexpr bool kSmemPhases = SUB == 4 && MR >= DSB_MESH_SMEM_PHASES_FROM;
+        __shared__ double s_ph[kSmemPhases ? MR : 1][kSmemPhases ? kBlock : 1];
+        if constexpr (kSmemPhases) {
+#pragma unroll
+            for (int m = 0; m < MR; ++m) s_ph[m][threadIdx.x] = ph[m];
+        }
         // phase accumulation with the post-step position (simulations.py:746-755 and alike)
         auto accumulate = [&](int t) {
 #pragma unroll
             for (int m = 0; m < MR; ++m) {
                 const double *g = p.grad + ((long long)m * p.n_t + t) * 3;
                 double gx = __ldg(g), gy = __ldg(g + 1), gz = __ldg(g + 2);
-                ph[m] = fma_(p.gamma_dt, fma_(gz, pos.z, fma_(gx, pos.x, mul_(gy, pos.y))), ph[m]);
+                if constexpr (kSmemPhases)
+                    s_ph[m][threadIdx.x] = fma_(p.gamma_dt, fma_(gz, pos.z, fma_(gx, pos.x, mul_(gy, pos.y))), s_ph[m][threadIdx.x]);
+                else
+                    ph[m] = fma_(p.gamma_dt, fma_(gz, pos.z, fma_(gx, pos.x, mul_(gy, pos.y))), ph[m]);
             }
         };
         if constexpr (SUB >= 1 && SUB <= 3 && ParkFlush<SUB>::value > 1) {
@@ -904,6 +919,10 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
         } else if constexpr (SUB == 4) {
             __shared__ MeshScratch s_scratch[kBlock / 32];
             mesh_walk<MAXC>(p, s_scratch[threadIdx.x >> 5], s_tab, active, p.t0, p.t1, pos, rng, exc, accumulate);
+            if constexpr (kSmemPhases) {
+#pragma unroll
+                for (int m = 0; m < MR; ++m) ph[m] = s_ph[m][threadIdx.x];
+            }
         } else {
             // the time loop is uniform over the block
             for (int t = p.t0; t < p.t1; ++t) {
