@@ -48,8 +48,8 @@ FP64_PER_WALKER_STEP = 120 + 25 + 4 * 1
 # (32), phase out (8), iter_exc (1)
 HBM_BYTES_PER_WALKER = 48 + 32 + 8 + 1
 # dram__bytes_read.sum + dram__bytes_write.sum of one walk_kernel<sphere,1> launch over 1e6 walkers
-# (profiles/r01_j_walk_sphere_ncu.md; independent of the number of steps in the launch)
-NCU_DRAM_BYTES_PER_LAUNCH = 41.09e6 + 0.32e6
+# (profiles/r01_k_walk_sphere_ncu.md; independent of the number of steps in the launch)
+NCU_DRAM_BYTES_PER_LAUNCH = 41.05e6 + 1.27e6
 
 
 def workload():

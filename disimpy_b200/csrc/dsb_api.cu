@@ -291,8 +291,8 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
         // accept points far outside its box: such triangles are marked and always tested exactly.
         const double *o = &tri[(size_t)f * dsb::kTriStride];
         const double det = std::fma(o[7], o[5], -(o[8] * o[4]));  // as ray_triangle forms it for ray = (1,0,0)
-        const double scale_yz = std::hypot(o[4], o[5]) * std::hypot(o[7], o[8]);
-        const bool edge_on = det != 0.0 && !(std::fabs(det) > 1e-9 * scale_yz);
+        const double scale2_yz = (o[4] * o[4] + o[5] * o[5]) * (o[7] * o[7] + o[8] * o[8]);
+        const bool edge_on = det != 0.0 && !(det * det > 1e-18 * scale2_yz);
         box[(size_t)f] = make_uint4((unsigned)f | (edge_on ? ~dsb::kEntryTriMask : 0u), lo[0] | (lo[1] << 16),
                                     lo[2] | (hi[0] << 16), hi[1] | (hi[2] << 16));
     }
