@@ -5,12 +5,14 @@
 #include "dsb_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -207,6 +209,23 @@ cudaError_t cache_malloc(T **out, size_t bytes)
 
 // ------------------------------------------------------------- mesh upload
 
+// fn(begin, end) over [0, n) in contiguous pieces on a few host threads (the re-layout loops below
+// are independent per element; a 1e6-triangle mesh has ~1e7 of them)
+template <typename Fn>
+void parallel_ranges(int64_t n, Fn fn)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)(hw ? hw : 1), n / 65536}));
+    if (n_threads <= 1) {
+        fn((int64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(fn, n * t / n_threads, n * (t + 1) / n_threads);
+    for (auto &th : pool) th.join();
+}
+
+
 struct MeshBuffers {
     double *tri = nullptr;
     double *normal = nullptr;
@@ -255,61 +274,82 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
     const int64_t n_cells = m.n_sv[0] * m.n_sv[1] * m.n_sv[2];
     if (n_cells > 0x7fffffffLL) return fail(DSB_EINVAL, "mesh: too many subvoxels");
     std::vector<double> tri((size_t)m.n_faces * dsb::kTriStride, 0.0);
-    for (int64_t f = 0; f < m.n_faces; ++f) {
-        const int64_t *idx = m.faces + 3 * f;
-        for (int c = 0; c < 3; ++c)
-            if (idx[c] < 0 || idx[c] >= m.n_vertices) return fail(DSB_EINVAL, "mesh: face index out of range");
-        const double *A = m.vertices + 3 * idx[0], *B = m.vertices + 3 * idx[1], *C = m.vertices + 3 * idx[2];
-        double *o = &tri[(size_t)f * dsb::kTriStride];
-        for (int c = 0; c < 3; ++c) {
-            o[c] = A[c];
-            o[3 + c] = B[c] - A[c];
-            o[6 + c] = C[c] - A[c];
+    std::atomic<bool> bad_index{false};
+    parallel_ranges(m.n_faces, [&](int64_t f0, int64_t f1) {
+        for (int64_t f = f0; f < f1; ++f) {
+            const int64_t *idx = m.faces + 3 * f;
+            bool ok = true;
+            for (int c = 0; c < 3; ++c) ok = ok && idx[c] >= 0 && idx[c] < m.n_vertices;
+            if (!ok) {
+                bad_index = true;
+                continue;
+            }
+            const double *A = m.vertices + 3 * idx[0], *B = m.vertices + 3 * idx[1], *C = m.vertices + 3 * idx[2];
+            double *o = &tri[(size_t)f * dsb::kTriStride];
+            for (int c = 0; c < 3; ++c) {
+                o[c] = A[c];
+                o[3 + c] = B[c] - A[c];
+                o[6 + c] = C[c] - A[c];
+            }
         }
-    }
+    });
+    if (bad_index) return fail(DSB_EINVAL, "mesh: face index out of range");
     // Box of every triangle on a 15-bit grid over [0, xs[-1]] x [0, ys[-1]] x [0, zs[-1]], rounded
     // outwards by a grid unit, for the kernels' pre-test; stored as (lo, 32767 - hi) halfwords so
     // that "boxes meet" is one direction of comparison for all six numbers.
     const double tops[3] = {m.xs[m.n_sv[0]], m.ys[m.n_sv[1]], m.zs[m.n_sv[2]]};
     std::vector<uint4> box((size_t)m.n_faces);
-    for (int64_t f = 0; f < m.n_faces; ++f) {
-        const int64_t *idx = m.faces + 3 * f;
-        unsigned lo[3], hi[3];
-        for (int k = 0; k < 3; ++k) {
-            const double a = m.vertices[3 * idx[0] + k], b = m.vertices[3 * idx[1] + k], c = m.vertices[3 * idx[2] + k];
-            const double mn = std::min(a, std::min(b, c)), mx = std::max(a, std::max(b, c));
-            const double scale = 32767.0 / tops[k];
-            double ql = std::floor(mn * scale) - 1.0, qh = std::ceil(mx * scale) + 1.0;
-            if (!(ql > 0.0)) ql = 0.0;        // also NaN: never filtered out
-            if (!(qh < 32767.0)) qh = 32767.0;
-            if (!(mn == mn) || !(mx == mx)) ql = 0.0, qh = 32767.0;
-            lo[k] = (unsigned)std::min(ql, 32767.0);
-            hi[k] = 32767u - (unsigned)std::max(qh, 0.0);
+    parallel_ranges(m.n_faces, [&](int64_t f0, int64_t f1) {
+        for (int64_t f = f0; f < f1; ++f) {
+            const int64_t *idx = m.faces + 3 * f;
+            unsigned lo[3], hi[3];
+            for (int k = 0; k < 3; ++k) {
+                const double a = m.vertices[3 * idx[0] + k], b = m.vertices[3 * idx[1] + k], c = m.vertices[3 * idx[2] + k];
+                const double mn = std::min(a, std::min(b, c)), mx = std::max(a, std::max(b, c));
+                const double scale = 32767.0 / tops[k];
+                double ql = std::floor(mn * scale) - 1.0, qh = std::ceil(mx * scale) + 1.0;
+                if (!(ql > 0.0)) ql = 0.0;        // also NaN: never filtered out
+                if (!(qh < 32767.0)) qh = 32767.0;
+                if (!(mn == mn) || !(mx == mx)) ql = 0.0, qh = 32767.0;
+                lo[k] = (unsigned)std::min(ql, 32767.0);
+                hi[k] = 32767u - (unsigned)std::max(qh, 0.0);
+            }
+            // Seen along +x (the sampler's ray, dsb_fill.cuh) a triangle whose projection on the yz plane
+            // is a sliver has a determinant that is mostly rounding error, and the reference's test may
+            // then accept points far outside its box: such triangles are marked and always tested exactly.
+            const double *o = &tri[(size_t)f * dsb::kTriStride];
+            const double det = std::fma(o[7], o[5], -(o[8] * o[4]));  // as ray_triangle forms it for ray = (1,0,0)
+            const double scale2_yz = (o[4] * o[4] + o[5] * o[5]) * (o[7] * o[7] + o[8] * o[8]);
+            const bool edge_on = det != 0.0 && !(det * det > 1e-18 * scale2_yz);
+            box[(size_t)f] = make_uint4((unsigned)f | (edge_on ? ~dsb::kEntryTriMask : 0u), lo[0] | (lo[1] << 16),
+                                        lo[2] | (hi[0] << 16), hi[1] | (hi[2] << 16));
         }
-        // Seen along +x (the sampler's ray, dsb_fill.cuh) a triangle whose projection on the yz plane is
-        // a sliver has a determinant that is mostly rounding error, and the reference's test may then
-        // accept points far outside its box: such triangles are marked and always tested exactly.
-        const double *o = &tri[(size_t)f * dsb::kTriStride];
-        const double det = std::fma(o[7], o[5], -(o[8] * o[4]));  // as ray_triangle forms it for ray = (1,0,0)
-        const double scale2_yz = (o[4] * o[4] + o[5] * o[5]) * (o[7] * o[7] + o[8] * o[8]);
-        const bool edge_on = det != 0.0 && !(det * det > 1e-18 * scale2_yz);
-        box[(size_t)f] = make_uint4((unsigned)f | (edge_on ? ~dsb::kEntryTriMask : 0u), lo[0] | (lo[1] << 16),
-                                    lo[2] | (hi[0] << 16), hi[1] | (hi[2] << 16));
-    }
+    });
     std::vector<int> tri_idx((size_t)m.n_triangle_indices);
     std::vector<uint4> entry((size_t)m.n_triangle_indices + 1);
-    for (int64_t i = 0; i < m.n_triangle_indices; ++i) {
-        if (m.triangle_indices[i] < 0 || m.triangle_indices[i] >= m.n_faces)
-            return fail(DSB_EINVAL, "mesh: triangle index out of range");
-        tri_idx[(size_t)i] = (int)m.triangle_indices[i];
-        entry[(size_t)i] = box[(size_t)m.triangle_indices[i]];
-    }
+    parallel_ranges(m.n_triangle_indices, [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; ++i) {
+            if (m.triangle_indices[i] < 0 || m.triangle_indices[i] >= m.n_faces) {
+                bad_index = true;
+                continue;
+            }
+            tri_idx[(size_t)i] = (int)m.triangle_indices[i];
+            entry[(size_t)i] = box[(size_t)m.triangle_indices[i]];
+        }
+    });
+    if (bad_index) return fail(DSB_EINVAL, "mesh: triangle index out of range");
     std::vector<int2> cells((size_t)n_cells);
-    for (int64_t c = 0; c < n_cells; ++c) {
-        int64_t a = m.subvoxel_indices[2 * c], b = m.subvoxel_indices[2 * c + 1];
-        if (a < 0 || b < a || b > m.n_triangle_indices) return fail(DSB_EINVAL, "mesh: subvoxel range out of bounds");
-        cells[(size_t)c] = make_int2((int)a, (int)b);
-    }
+    parallel_ranges(n_cells, [&](int64_t c0, int64_t c1) {
+        for (int64_t c = c0; c < c1; ++c) {
+            int64_t a = m.subvoxel_indices[2 * c], b = m.subvoxel_indices[2 * c + 1];
+            if (a < 0 || b < a || b > m.n_triangle_indices) {
+                bad_index = true;
+                continue;
+            }
+            cells[(size_t)c] = make_int2((int)a, (int)b);
+        }
+    });
+    if (bad_index) return fail(DSB_EINVAL, "mesh: subvoxel range out of bounds");
     DSB_CUDA(cache_malloc(&mb.tri, tri.size() * sizeof(double)));
     DSB_CUDA(cache_malloc(&mb.tri_idx, (tri_idx.size() + 1) * sizeof(int)));
     DSB_CUDA(cache_malloc(&mb.entry, entry.size() * sizeof(uint4)));
@@ -369,23 +409,50 @@ int build_fill_columns(MeshBuffers &mb)
     const int64_t n0 = mb.n_sv[0], n1 = mb.n_sv[1], n2 = mb.n_sv[2];
     const int64_t n_cols = n1 * n2;
     std::vector<int> start((size_t)n_cols + 1), cnt((size_t)(n_cols * n0));
-    std::vector<uint4> entry;
-    entry.reserve(mb.h_tri_idx.size());
-    std::vector<int64_t> seen_in(mb.h_box.size(), -1);
-    for (int64_t col = 0; col < n_cols; ++col) {
-        const int64_t y = col / n2, z = col % n2;
-        const size_t begin = entry.size();
-        start[(size_t)col] = (int)begin;
-        for (int64_t x = n0 - 1; x >= 0; --x) {
-            const int2 c = mb.h_cells[(size_t)((x * n1 + y) * n2 + z)];
-            for (int i = c.x; i < c.y; ++i) {
-                const int t = mb.h_tri_idx[(size_t)i];
-                if (seen_in[(size_t)t] != col) {
-                    seen_in[(size_t)t] = col;
-                    entry.push_back(mb.h_box[(size_t)t]);
+    // pieces of consecutive columns, each on its own thread with its own "seen in this column" marks
+    const int n_pieces = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::max(1u, std::thread::hardware_concurrency()),
+                                                                    (int64_t)mb.h_tri_idx.size() / 262144}));
+    std::vector<std::vector<uint4>> piece_entry((size_t)n_pieces);
+    std::vector<std::vector<int>> piece_start((size_t)n_pieces);
+    auto work = [&](int piece) {
+        const int64_t col0 = n_cols * piece / n_pieces, col1 = n_cols * (piece + 1) / n_pieces;
+        std::vector<uint4> &out = piece_entry[(size_t)piece];
+        std::vector<int> &st = piece_start[(size_t)piece];
+        std::vector<int64_t> seen_in(mb.h_box.size(), -1);
+        for (int64_t col = col0; col < col1; ++col) {
+            const int64_t y = col / n2, z = col % n2;
+            const size_t begin = out.size();
+            st.push_back((int)begin);
+            for (int64_t x = n0 - 1; x >= 0; --x) {
+                const int2 c = mb.h_cells[(size_t)((x * n1 + y) * n2 + z)];
+                for (int i = c.x; i < c.y; ++i) {
+                    const int t = mb.h_tri_idx[(size_t)i];
+                    if (seen_in[(size_t)t] != col) {
+                        seen_in[(size_t)t] = col;
+                        out.push_back(mb.h_box[(size_t)t]);
+                    }
                 }
+                cnt[(size_t)(col * n0 + x)] = (int)(out.size() - begin);
             }
-            cnt[(size_t)(col * n0 + x)] = (int)(entry.size() - begin);
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int piece = 1; piece < n_pieces; ++piece) pool.emplace_back(work, piece);
+        work(0);
+        for (auto &th : pool) th.join();
+    }
+    std::vector<uint4> entry;
+    {
+        size_t total = 0;
+        for (auto &v : piece_entry) total += v.size();
+        entry.reserve(total + 1);
+        for (int piece = 0; piece < n_pieces; ++piece) {
+            const int64_t col0 = n_cols * piece / n_pieces;
+            const int base = (int)entry.size();
+            for (size_t k = 0; k < piece_start[(size_t)piece].size(); ++k)
+                start[(size_t)col0 + k] = base + piece_start[(size_t)piece][k];
+            entry.insert(entry.end(), piece_entry[(size_t)piece].begin(), piece_entry[(size_t)piece].end());
         }
     }
     start[(size_t)n_cols] = (int)entry.size();
