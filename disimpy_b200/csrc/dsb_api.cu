@@ -207,6 +207,93 @@ cudaError_t cache_malloc(T **out, size_t bytes)
     return cache_malloc(reinterpret_cast<void **>(out), bytes);
 }
 
+// ------------------------------------------------------------- pinned host scratch
+
+// The mesh re-layout below fills a few hundred MB of host arrays per handle.  Fresh pages for
+// them cost more than the arithmetic (first-touch faults), and pageable memory uploads at a
+// fraction of the PCIe rate, so these arrays are page-locked blocks kept by size like the device
+// buffers above and handed from one handle to the next.
+struct HostCache {
+    std::mutex mu;
+    std::multimap<size_t, void *> idle;
+    std::map<void *, size_t> live;
+    size_t idle_bytes = 0;
+    static constexpr size_t kMaxIdleBytes = size_t(4) << 30;
+} g_host_cache;
+
+void *host_cache_malloc(size_t bytes)
+{
+    bytes = std::max<size_t>(bytes, 1);
+    {
+        std::lock_guard<std::mutex> lk(g_host_cache.mu);
+        auto it = g_host_cache.idle.find(bytes);
+        if (it != g_host_cache.idle.end()) {
+            void *p = it->second;
+            g_host_cache.idle.erase(it);
+            g_host_cache.idle_bytes -= bytes;
+            g_host_cache.live[p] = bytes;
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_host_cache.mu);
+    g_host_cache.live[p] = bytes;
+    return p;
+}
+
+void host_cache_free(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_host_cache.mu);
+    auto it = g_host_cache.live.find(p);
+    if (it == g_host_cache.live.end()) {
+        cudaFreeHost(p);
+        return;
+    }
+    const size_t bytes = it->second;
+    g_host_cache.live.erase(it);
+    if (g_host_cache.idle_bytes + bytes > HostCache::kMaxIdleBytes) {
+        cudaFreeHost(p);
+        return;
+    }
+    g_host_cache.idle.insert({bytes, p});
+    g_host_cache.idle_bytes += bytes;
+}
+
+// move-only array in that memory (uninitialised)
+template <typename T>
+struct HostBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    HostBuf() = default;
+    explicit HostBuf(size_t count) : p(static_cast<T *>(host_cache_malloc(std::max<size_t>(count, 1) * sizeof(T)))), n(count) {}
+    HostBuf(HostBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    HostBuf &operator=(HostBuf &&o) noexcept
+    {
+        if (this != &o) {
+            host_cache_free(p);
+            p = o.p;
+            n = o.n;
+            o.p = nullptr;
+            o.n = 0;
+        }
+        return *this;
+    }
+    HostBuf(const HostBuf &) = delete;
+    HostBuf &operator=(const HostBuf &) = delete;
+    ~HostBuf() { host_cache_free(p); }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+    bool ok() const { return p != nullptr; }
+};
+
 // ------------------------------------------------------------- mesh upload
 
 // fn(begin, end) over [0, n) in contiguous pieces on a few host threads (the re-layout loops below
@@ -235,9 +322,9 @@ struct MeshBuffers {
     double *xs = nullptr, *ys = nullptr, *zs = nullptr;
     dsb::MeshDev dev{};
     // host copies the initial-position sampler's column lists are built from on first use
-    std::vector<int2> h_cells;
-    std::vector<int> h_tri_idx;
-    std::vector<uint4> h_box;
+    HostBuf<int2> h_cells;
+    HostBuf<int> h_tri_idx;
+    HostBuf<uint4> h_box;
     int64_t n_sv[3] = {0, 0, 0};
     int *col_start = nullptr, *col_cnt = nullptr;
     uint4 *col_entry = nullptr;
@@ -273,7 +360,13 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
         if (m.n_sv[k] <= 0 || m.n_sv[k] > 1 << 20) return fail(DSB_EINVAL, "mesh: n_sv out of range");
     const int64_t n_cells = m.n_sv[0] * m.n_sv[1] * m.n_sv[2];
     if (n_cells > 0x7fffffffLL) return fail(DSB_EINVAL, "mesh: too many subvoxels");
-    std::vector<double> tri((size_t)m.n_faces * dsb::kTriStride, 0.0);
+    HostBuf<double> tri((size_t)m.n_faces * dsb::kTriStride);
+    HostBuf<uint4> box((size_t)m.n_faces);
+    HostBuf<int> tri_idx((size_t)m.n_triangle_indices);
+    HostBuf<uint4> entry((size_t)m.n_triangle_indices + 1);
+    HostBuf<int2> cells((size_t)n_cells);
+    if (!tri.ok() || !box.ok() || !tri_idx.ok() || !entry.ok() || !cells.ok())
+        return fail(DSB_ENOMEM, "mesh: no page-locked host memory for the re-layout");
     std::atomic<bool> bad_index{false};
     parallel_ranges(m.n_faces, [&](int64_t f0, int64_t f1) {
         for (int64_t f = f0; f < f1; ++f) {
@@ -291,6 +384,7 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
                 o[3 + c] = B[c] - A[c];
                 o[6 + c] = C[c] - A[c];
             }
+            for (int c = 9; c < dsb::kTriStride; ++c) o[c] = 0.0;
         }
     });
     if (bad_index) return fail(DSB_EINVAL, "mesh: face index out of range");
@@ -298,7 +392,6 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
     // outwards by a grid unit, for the kernels' pre-test; stored as (lo, 32767 - hi) halfwords so
     // that "boxes meet" is one direction of comparison for all six numbers.
     const double tops[3] = {m.xs[m.n_sv[0]], m.ys[m.n_sv[1]], m.zs[m.n_sv[2]]};
-    std::vector<uint4> box((size_t)m.n_faces);
     parallel_ranges(m.n_faces, [&](int64_t f0, int64_t f1) {
         for (int64_t f = f0; f < f1; ++f) {
             const int64_t *idx = m.faces + 3 * f;
@@ -325,8 +418,7 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
                                         lo[2] | (hi[0] << 16), hi[1] | (hi[2] << 16));
         }
     });
-    std::vector<int> tri_idx((size_t)m.n_triangle_indices);
-    std::vector<uint4> entry((size_t)m.n_triangle_indices + 1);
+    entry[(size_t)m.n_triangle_indices] = make_uint4(0u, 0u, 0u, 0u);
     parallel_ranges(m.n_triangle_indices, [&](int64_t i0, int64_t i1) {
         for (int64_t i = i0; i < i1; ++i) {
             if (m.triangle_indices[i] < 0 || m.triangle_indices[i] >= m.n_faces) {
@@ -338,7 +430,6 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
         }
     });
     if (bad_index) return fail(DSB_EINVAL, "mesh: triangle index out of range");
-    std::vector<int2> cells((size_t)n_cells);
     parallel_ranges(n_cells, [&](int64_t c0, int64_t c1) {
         for (int64_t c = c0; c < c1; ++c) {
             int64_t a = m.subvoxel_indices[2 * c], b = m.subvoxel_indices[2 * c + 1];
@@ -363,7 +454,7 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
     dsb::tri_normal_kernel<<<(unsigned)((m.n_faces + 255) / 256), 256>>>(mb.tri, (long long)m.n_faces, mb.normal);
     DSB_CUDA(cudaGetLastError());
     DSB_CUDA(cudaDeviceSynchronize());
-    if (!tri_idx.empty())
+    if (tri_idx.size() > 0)
         DSB_CUDA(cudaMemcpy(mb.tri_idx, tri_idx.data(), tri_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaMemcpy(mb.cell_rng, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaMemcpy(mb.xs, m.xs, (m.n_sv[0] + 1) * sizeof(double), cudaMemcpyHostToDevice));
@@ -442,21 +533,22 @@ int build_fill_columns(MeshBuffers &mb)
         work(0);
         for (auto &th : pool) th.join();
     }
-    std::vector<uint4> entry;
+    size_t total = 0;
+    for (auto &v : piece_entry) total += v.size();
+    HostBuf<uint4> entry(total + 1);
+    if (!entry.ok()) return fail(DSB_ENOMEM, "mesh: no page-locked host memory for the column lists");
     {
-        size_t total = 0;
-        for (auto &v : piece_entry) total += v.size();
-        entry.reserve(total + 1);
+        size_t at = 0;
         for (int piece = 0; piece < n_pieces; ++piece) {
             const int64_t col0 = n_cols * piece / n_pieces;
-            const int base = (int)entry.size();
             for (size_t k = 0; k < piece_start[(size_t)piece].size(); ++k)
-                start[(size_t)col0 + k] = base + piece_start[(size_t)piece][k];
-            entry.insert(entry.end(), piece_entry[(size_t)piece].begin(), piece_entry[(size_t)piece].end());
+                start[(size_t)col0 + k] = (int)at + piece_start[(size_t)piece][k];
+            std::copy(piece_entry[(size_t)piece].begin(), piece_entry[(size_t)piece].end(), entry.data() + at);
+            at += piece_entry[(size_t)piece].size();
         }
     }
-    start[(size_t)n_cols] = (int)entry.size();
-    entry.push_back(make_uint4(0u, 0xffffffffu, 0xffffffffu, 0xffffffffu));
+    start[(size_t)n_cols] = (int)total;
+    entry[total] = make_uint4(0u, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     DSB_CUDA(cache_malloc(&mb.col_start, start.size() * sizeof(int)));
     DSB_CUDA(cache_malloc(&mb.col_cnt, cnt.size() * sizeof(int)));
     DSB_CUDA(cache_malloc(&mb.col_entry, entry.size() * sizeof(uint4)));
@@ -678,6 +770,10 @@ int dsb_release_cache(void)
     g_cache.idle.clear();
     g_cache.idle_bytes = 0;
     cudaSetDevice(dev);
+    std::lock_guard<std::mutex> hk(g_host_cache.mu);
+    for (auto &kv : g_host_cache.idle) cudaFreeHost(kv.second);
+    g_host_cache.idle.clear();
+    g_host_cache.idle_bytes = 0;
     return DSB_OK;
 }
 const char *dsb_version(void) { return "disimpy_b200 0.1 (sm_100a)"; }
