@@ -245,6 +245,33 @@ def secondary_workloads(device, fp64_peak, sm_mhz):
     return out
 
 
+def config5_shard():
+    """BASELINE config 5 as one GPU sees it: the 1 048 576-triangle periodic mesh, 180 waveforms,
+    1000 steps and the 1.25e7 walkers a rank of the 8-GPU job holds, through simulation() (mesh
+    upload, initial positions drawn on the GPU, walk, signal back).  The whole job is this on
+    every rank (profiles/r01_k_config5.json has the 2- and 8-GPU runs)."""
+    from disimpy_b200 import gradients, meshgen, simulations, substrates
+    dirs = meshgen.fibonacci_sphere(60)
+    g, dt = gradients.pgse(10e-3, 30e-3, 1000, [1e9] * 60 + [2e9] * 60 + [3e9] * 60, np.vstack([dirs, dirs, dirs]))
+    v, f, pad, _ = meshgen.tube_lattice(16, 16, 5e-6, 12e-6, 40e-6, 128, 16)
+    t0 = time.perf_counter()
+    sub = substrates.mesh(v, f, True, padding=pad, init_pos="extra", n_sv=np.array([100, 100, 50]), quiet=True)
+    mesh_s = time.perf_counter() - t0
+    n = 12_500_000
+    simulations.simulation(100_000, DIFFUSIVITY, g, dt, sub, seed=SEED, quiet=True)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        sig = simulations.simulation(n, DIFFUSIVITY, g, dt, sub, seed=SEED, quiet=True)
+        e2e_s = time.perf_counter() - t0
+        best = e2e_s if best is None else min(best, e2e_s)
+    return {"workload": "BASELINE config 5, one GPU's share of the 8-GPU job: periodic mesh of 16x16 tubes (%d triangles, "
+                        "n_sv 100x100x50), init_pos extra, %d walkers x 1000 steps x 180 waveforms, through simulation()"
+                        % (len(f), n),
+            "value": n * g.shape[1] / best, "unit": UNIT, "e2e_ms": 1e3 * best,
+            "substrates_mesh_ms": 1e3 * mesh_s, "signal0_over_n": float(sig[0]) / n}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's algorithm on the host cores (oracle port; the Python
     reference itself only has a GPU path and a ~600 walker-steps/s Numba simulator)."""
@@ -437,6 +464,10 @@ def main():
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
         secondary = secondary_workloads(local_rank, peak.value, (clocks or {}).get("sm_mhz"))
+        try:
+            secondary.append(config5_shard())
+        except Exception as e:  # never let the extra workload cost the bench line
+            secondary.append({"workload": "BASELINE config 5 shard", "error": repr(e)})
 
     if rank == 0:
         line = {
