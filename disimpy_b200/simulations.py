@@ -627,6 +627,18 @@ def _walk_pipelined(walk, substrate, owned, seed):
 _SHARDED_FILL_MIN = 1 << 20
 
 
+def _round_rows(counts, have, lo, n_local):
+    """Where a round's accepted points go: rank r accepted counts[r] points, in thread order; they
+    become the global points have, have + 1, ... in rank order.  Yields (rank, first row in that
+    rank's block, first local row, how many) for the pieces that fall into [lo, lo + n_local)."""
+    start = have
+    for r, c in enumerate(counts):
+        a, b = max(start, lo), min(start + c, lo + n_local)
+        if a < b:
+            yield r, a - start, a - lo, b - a
+        start += c
+
+
 def _fill_mesh_sharded(walk, substrate, n_points, lo, n_local, seed, rank, world, dist):
     """The reference's mesh sampler (disimpy/simulations.py:505-579) with its threads dealt to the
     ranks: in every round rank r evaluates threads shard_range(n_points, r, world), the accepted
@@ -649,20 +661,19 @@ def _fill_mesh_sharded(walk, substrate, n_points, lo, n_local, seed, rank, world
             n_acc = walk.fill_shard_round(substrate.voxel_size, intra, accepted.data_ptr())
             dist.all_gather_into_tensor(counts, torch.tensor([n_acc], dtype=torch.int64, device=dev))
             dist.all_gather_into_tensor(everyone, accepted)
-            start = have
-            for r, c in enumerate(counts.tolist()):
-                a, b = max(start, lo), min(start + c, lo + n_local)
-                if a < b:
-                    mine[a - lo:b - lo] = everyone[r, a - start:b - start]
-                start += c
-            have = start
+            round_counts = counts.tolist()
+            for r, src, dst, k in _round_rows(round_counts, have, lo, n_local):
+                mine[dst:dst + k] = everyone[r, src:src + k]
+            have += sum(round_counts)
+            # the library writes `accepted` on its own stream in the next round: the all-gather
+            # and the copies above must be through with it
+            torch.cuda.synchronize(dev)
             if have >= n_points:
                 break
         else:
             raise RuntimeError("fill_mesh: no acceptable points (is the surface closed?)")
     finally:
         walk.fill_shard_end()
-    torch.cuda.synchronize(dev)
     walk.set_positions_dev(mine.data_ptr())
     walk.sync()
 

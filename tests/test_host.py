@@ -410,3 +410,29 @@ def test_protocol_factorisation():
     bad = g.copy()
     bad[3, 7, 1] = np.nan
     assert factor(bad)[0] == 0                                              # non-finite samples: general path
+
+
+def test_sharded_sampler_row_assembly():
+    """simulations._round_rows: the accepted points of every rank and round, concatenated round
+    after round in rank order and cut to n points, land in the right local rows of every rank."""
+    from disimpy_b200 import simulations
+    rs = np.random.RandomState(3)
+    for world in (1, 2, 3, 8):
+        n = int(rs.randint(50, 400))
+        rounds = []          # per round, per rank: the global "point ids" that rank accepted
+        next_id, total = 0, 0
+        while total < n:
+            counts = [int(c) for c in rs.randint(0, 40, size=world)]
+            rounds.append([list(range(next_id + sum(counts[:r]), next_id + sum(counts[:r + 1]))) for r in range(world)])
+            next_id += sum(counts)
+            total += sum(counts)
+        for rank in range(world):
+            lo, hi = simulations.shard_range(n, rank, world)
+            mine = np.full(hi - lo, -1)
+            have = 0
+            for per_rank in rounds:
+                counts = [len(x) for x in per_rank]
+                for r, src, dst, k in simulations._round_rows(counts, have, lo, hi - lo):
+                    mine[dst:dst + k] = per_rank[r][src:src + k]
+                have += sum(counts)
+            assert np.array_equal(mine, np.arange(lo, hi))
