@@ -7,8 +7,10 @@ accumulation and the sum of cos(phase) run inside libdisimpy_b200.so (hand-writt
 CUDA behind the C ABI in include/disimpy_b200.h).  There is no CPU fallback.
 
 Multi-GPU: when ``torch.distributed`` is initialised, every rank simulates the contiguous
-walker range ``[rank*N/W, (rank+1)*N/W)`` with RNG subsequence offset = first global walker
-index, and the signal (+ valid-walker count) is summed with one all-reduce; results do not
+walker range ``[rank*N/W, (rank+1)*N/W)`` (or, when the initial positions come from the
+sequential host stream, every W-th part of 131072 walkers) with the walkers' global RNG
+subsequences, and the signal (+ valid-walker count) is summed with one all-reduce; the mesh
+sampler's threads are dealt to the ranks and its accepted points all-gathered.  Results do not
 depend on the number of ranks (up to floating-point summation order of the signal).
 """
 
