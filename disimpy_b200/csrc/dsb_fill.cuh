@@ -11,7 +11,8 @@ constexpr int kMaxRayHits = 1000;  // simulations.py:462-467
 
 // The reference's loop as it is: every listed triangle of every cell from the point's cell to the
 // end of the grid along +x is ray-tested, distinct hits are counted, the thread gives up at 1000.
-// Out of line: only points with more than kFillFastHits crossings come here.
+// Out of line: only points with 1000 or more crossings, or with cell ranges the column walk does
+// not cover, come here.
 __device__ __noinline__ bool fill_ray_parity_reference(const MeshDev &g, const Vec3 &pt, int lx, int ux, int ly, int uy,
                                                        int lz, int uz, bool &abandoned)
 {
@@ -59,7 +60,7 @@ struct FillColumns {
 constexpr int kFillWarps = 4;
 
 // 32 proposed points per warp, one per lane; their columns are then scanned one point after the
-// other by the whole warp, 32 entries at a time.  A listed triangle is ray-tested only if its box
+// other by the whole warp, 64 entries per iteration.  A listed triangle is ray-tested only if its box
 // (15-bit grid, rounded outwards) meets the ray's: a triangle the reference counts is hit at
 // u, v in [0, 1], so the point's y and z lie within rounding of the triangle's, and its x below the
 // triangle's top; edge-on triangles, for which rounding says nothing, are marked at upload and
