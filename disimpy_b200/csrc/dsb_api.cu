@@ -609,6 +609,17 @@ constexpr size_t many_meas_smem()
 template <int SUB, int MAXC>
 void launch_walk_cells(const dsb::KParams &kp, int grid, cudaStream_t st)
 {
+#ifdef DSB_TWO_WALKERS
+    if constexpr (SUB >= 1 && SUB <= 3) {   // experiment: two walkers per lane (dsb_kernels.cuh)
+        switch (kp.n_meas <= dsb::kMaxRegMeas ? kp.n_meas : 0) {
+        case 1: dsb::walk2_kernel<SUB, 1><<<grid, dsb::kBlock / 2, 0, st>>>(kp); return;
+        case 2: dsb::walk2_kernel<SUB, 2><<<grid, dsb::kBlock / 2, 0, st>>>(kp); return;
+        case 3: dsb::walk2_kernel<SUB, 3><<<grid, dsb::kBlock / 2, 0, st>>>(kp); return;
+        case 4: dsb::walk2_kernel<SUB, 4><<<grid, dsb::kBlock / 2, 0, st>>>(kp); return;
+        default: break;
+        }
+    }
+#endif
     switch (kp.n_meas <= dsb::kMaxRegMeas ? kp.n_meas : 0) {
     case 1: dsb::walk_kernel<SUB, 1, MAXC><<<grid, dsb::kBlock, 0, st>>>(kp); break;
     case 2: dsb::walk_kernel<SUB, 2, MAXC><<<grid, dsb::kBlock, 0, st>>>(kp); break;
