@@ -436,3 +436,16 @@ def test_sharded_sampler_row_assembly():
                     mine[dst:dst + k] = per_rank[r][src:src + k]
                 have += sum(counts)
             assert np.array_equal(mine, np.arange(lo, hi))
+
+
+def test_tools_and_entry_points_compile():
+    """Every script a maintainer or the driver runs on the GPU box is at least valid Python here
+    (they cannot be executed without a GPU)."""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "tools", "*.py"))) + [os.path.join(root, "bench.py"),
+                                                                      os.path.join(root, "__graft_entry__.py")]
+    assert len(files) > 5
+    for f in files:
+        py_compile.compile(f, doraise=True)
