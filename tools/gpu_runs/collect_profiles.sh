@@ -1,6 +1,6 @@
 #!/bin/bash
 # What a round's measurements are made of (run from the repo root under gpurun, one B200):
-#   gpurun --timeout 2400 -- 'bash tools/gpu_runs/collect_profiles.sh r01_g'
+#   gpurun --timeout 2400 -- 'bash tools/gpu_runs/collect_profiles.sh r02_a'
 # then, back in the container:  python tools/summarize_profiles.py <tag> gpurun_out/launches_<tag>.csv ...
 # Every command is bounded by `timeout`: a hung kernel must not hold the box.
 tag=${1:-rXX}
@@ -22,3 +22,9 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:walk
 # the same protocol on the general many-measurement path (tensor-core phase product)
 DISIMPY_B200_LOWRANK=0 timeout 300 ncu --set full --clock-control none --import-source on -k regex:walk_kernel -s 1 -c 1 -f \
     -o gpurun_out/prof_${tag}_sphere180_general python tools/kbench.py sphere180 2>&1 | tail -2
+# the mesh sampler on the config-5 mesh (1.25e7 proposed points per launch)
+unset KBENCH_NT KBENCH_N
+REPS=1 NTOT=12500000 WALK=0 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fill_mesh_kernel -c 1 -f \
+    -o gpurun_out/prof_${tag}_fill python tools/sampler_bench.py 2>&1 | tail -2
+# BASELINE config 5 as one GPU of the 8-GPU job sees it, through simulation()
+timeout 400 python tools/config5.py > gpurun_out/config5_${tag}.log 2>&1; tail -3 gpurun_out/config5_${tag}.log
