@@ -113,7 +113,9 @@ inline uint64_t splitmix64(uint64_t seed)
 std::mutex g_pow_mu;
 ulonglong2 *g_dev_pows[64] = {nullptr};  // per device ordinal
 
-int device_jump_powers(int device, ulonglong2 **out)
+// The upload is ordered on `st` (the stream the caller launches rng_init_kernel on) and waited for
+// before the table is published: later callers on other non-blocking streams may use it at once.
+int device_jump_powers(int device, cudaStream_t st, ulonglong2 **out)
 {
     if (device < 0 || device >= 64) return fail(DSB_EINVAL, "device ordinal out of range");
     std::lock_guard<std::mutex> lk(g_pow_mu);
@@ -121,7 +123,8 @@ int device_jump_powers(int device, ulonglong2 **out)
         const std::vector<HState> &p = jump_powers();
         ulonglong2 *d = nullptr;
         DSB_CUDA(cudaMalloc(&d, p.size() * sizeof(HState)));
-        DSB_CUDA(cudaMemcpy(d, p.data(), p.size() * sizeof(HState), cudaMemcpyHostToDevice));
+        DSB_CUDA(cudaMemcpyAsync(d, p.data(), p.size() * sizeof(HState), cudaMemcpyHostToDevice, st));
+        DSB_CUDA(cudaStreamSynchronize(st));
         g_dev_pows[device] = d;
     }
     *out = g_dev_pows[device];
@@ -132,7 +135,7 @@ int launch_rng_init(int device, uint64_t seed, uint64_t start, int64_t n, ulongl
 {
     if (n <= 0) return DSB_OK;
     ulonglong2 *pows = nullptr;
-    int rc = device_jump_powers(device, &pows);
+    int rc = device_jump_powers(device, st, &pows);
     if (rc) return rc;
     int64_t blocks = (n + 256 * dsb::kRngInitRun - 1) / (256 * dsb::kRngInitRun);
     dsb::rng_init_kernel<<<(unsigned)blocks, 256, 0, st>>>(splitmix64(seed), start, (long long)n, pows, d_out);
@@ -460,6 +463,9 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
     DSB_CUDA(cudaMemcpy(mb.xs, m.xs, (m.n_sv[0] + 1) * sizeof(double), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaMemcpy(mb.ys, m.ys, (m.n_sv[1] + 1) * sizeof(double), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaMemcpy(mb.zs, m.zs, (m.n_sv[2] + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    // copies from pageable memory may return before the DMA lands, and the handle's streams do not
+    // synchronise with the legacy stream: wait here
+    DSB_CUDA(cudaDeviceSynchronize());
     dsb::MeshDev &d = mb.dev;
     d.tri = mb.tri;
     d.normal = mb.normal;
@@ -555,6 +561,7 @@ int build_fill_columns(MeshBuffers &mb)
     DSB_CUDA(cudaMemcpy(mb.col_start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaMemcpy(mb.col_cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaMemcpy(mb.col_entry, entry.data(), entry.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaDeviceSynchronize());  // (as in upload_mesh)
     mb.columns.start = mb.col_start;
     mb.columns.cnt = mb.col_cnt;
     mb.columns.entry = mb.col_entry;
@@ -882,10 +889,11 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
     DSB_TRY(cache_malloc(&s->d_rng, sizeof(unsigned long long) * 2 * N));
     DSB_TRY(cache_malloc(&s->d_rng0, sizeof(unsigned long long) * 2 * N));
     DSB_TRY(cache_malloc(&s->d_exc, N));
-    DSB_TRY(cudaMemcpy(s->d_grad, gradient, sizeof(double) * 3 * Mw * T, cudaMemcpyHostToDevice));
+    // uploads are ordered on the handle's own (non-blocking) stream: the kernels that read them run there
+    DSB_TRY(cudaMemcpyAsync(s->d_grad, gradient, sizeof(double) * 3 * Mw * T, cudaMemcpyHostToDevice, s->stream));
     if (s->rank > 0) {
         DSB_TRY(cache_malloc(&s->d_u, sizeof(double) * M * s->rank));
-        DSB_TRY(cudaMemcpy(s->d_u, lr_u.data(), sizeof(double) * M * s->rank, cudaMemcpyHostToDevice));
+        DSB_TRY(cudaMemcpyAsync(s->d_u, lr_u.data(), sizeof(double) * M * s->rank, cudaMemcpyHostToDevice, s->stream));
     }
     if (Mw > dsb::kMaxRegMeas) {
         // chunk-major copy for the many-measurement kernels: (chunk, measurement, step in chunk, xyz),
@@ -898,8 +906,10 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
                 for (int c = 0; c < 3; ++c)
                     gc[(size_t)(((t / C) * Mw + m) * L + (t % C) * 3 + c)] = gamma_dt * gradient[(m * T + t) * 3 + c];
         DSB_TRY(cache_malloc(&s->d_grad_chunked, gc.size() * sizeof(double)));
-        DSB_TRY(cudaMemcpy(s->d_grad_chunked, gc.data(), gc.size() * sizeof(double), cudaMemcpyHostToDevice));
+        DSB_TRY(cudaMemcpyAsync(s->d_grad_chunked, gc.data(), gc.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        DSB_TRY(cudaStreamSynchronize(s->stream));  // gc is a local
     }
+    DSB_TRY(cudaStreamSynchronize(s->stream));  // the sources (caller's gradient, lr_u, lr_v) are free again
 #undef DSB_TRY
     if (params->substrate == DSB_MESH) {
         rc = upload_mesh(params->mesh, s->mesh);

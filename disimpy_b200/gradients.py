@@ -2,8 +2,7 @@
 
 A gradient array has shape (n_measurements, n_time_points, 3) in T/m, exactly what
 ``simulations.simulation`` takes.  Same function names and argument meaning as
-disimpy/gradients.py:13-173 so that scripts written for the reference keep working; the
-Camino scheme loader is not part of this package.
+disimpy/gradients.py:13-173 so that scripts written for the reference keep working.
 """
 
 import numpy as np
@@ -36,7 +35,9 @@ def calc_q(gradient, dt):
 def calc_b(gradient, dt):
     """b-value of every measurement: integral of |q|^2 dt (trapezoid rule)."""
     q2 = np.linalg.norm(calc_q(gradient, dt), axis=2) ** 2
-    return dt * (q2[:, 1:] + q2[:, :-1]).sum(axis=1) / 2
+    # np.trapz's evaluation order (disimpy/gradients.py:89), so that set_b / pgse return arrays
+    # bit-identical to the reference's
+    return (dt * (q2[:, 1:] + q2[:, :-1]) / 2.0).sum(axis=1)
 
 
 def set_b(gradient, dt, b):
@@ -73,3 +74,19 @@ def pgse(delta, DELTA, n_t, bvals, bvecs):
     Rs = np.stack([utils.vec2vec_rotmat(np.array([1.0, 0.0, 0.0]), np.asarray(v, dtype=float))
                    for v in bvecs])
     return rotate_gradient(gradient, Rs), dt
+
+
+def load_camino_scheme_file(path):
+    """Gradient array and time step from a Camino general-waveform scheme file
+    (disimpy/gradients.py:182-212): first line 'VERSION: GRADIENT_WAVEFORM', then one row per
+    measurement: K, dt, g_x1 g_y1 g_z1 g_x2 ...; all rows must share one time step."""
+    with open(path, "r") as file:
+        if file.readline().strip() != "VERSION: GRADIENT_WAVEFORM":
+            raise Exception("The scheme file does not start with 'VERSION: GRADIENT_WAVEFORM'")
+    scheme = np.loadtxt(path, skiprows=1, ndmin=2)
+    dts = scheme[:, 1]
+    if len(set(dts)) != 1:
+        raise Exception(
+            "Not all rows of the scheme file have the same time step duration. "
+            "Disimpy does not support scheme files with multiple time step durations.")
+    return scheme[:, 2:].reshape(len(scheme), -1, 3), dts[0]

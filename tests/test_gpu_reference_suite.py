@@ -104,7 +104,7 @@ def test_sphere_and_ellipsoid_trajectories(tmp_path):  # :587-600, :657-683
     npt.assert_almost_equal(sig_ell, sig_sphere)
 
 
-def test_mesh_diffusion():  # :686-812 (the neuron model, 7.5 MB in the reference tree, is not shipped here)
+def test_mesh_diffusion():  # :686-812 (the neuron-model part, :814-832, is test_neuron_model_no_leak below)
     from disimpy_b200 import simulations, substrates
     meshes = load_golden("ref_meshes")
     misst = load_golden("ref_misst_signals")["cylinder_30ms"]
@@ -137,3 +137,75 @@ def test_mesh_diffusion():  # :686-812 (the neuron model, 7.5 MB in the referenc
             assert np.min(pos[:, 2]) < 0
             assert np.max(pos[:, 2]) > substrate.voxel_size[2]
             assert np.max(np.linalg.norm(pos[:, 0:2] - np.max(substrate.vertices, axis=0)[0:2] / 2, axis=1)) < r
+
+
+def _real_mesh(name):
+    m = load_golden("ref_real_meshes")
+    return m[name + "_vertices"], m[name + "_faces"].astype(np.int64)
+
+
+@pytest.mark.parametrize("dt", [1e-5, 1e-3, 1e-1])
+def test_neuron_model_no_leak(dt):  # :814-832
+    """The reference's neuron-model test: 29 688 irregular triangles with float32 vertices, default
+    n_sv, init_pos='intra', periodic.  dt = 1e-1 gives 35 um steps that span many grid cells (the
+    per-lane search on a real mesh).  The reference's containment assertion, and -- beyond it --
+    final positions bit for bit and the signal against the oracle."""
+    from disimpy_b200 import simulations, substrates
+    from oracle import oracle as O
+    vertices, faces = _real_mesh("neuron_model")
+    assert vertices.dtype == np.float32
+    n_s, n_t = int(1e3), int(1e2)
+    gradient = np.ones((1, n_t, 3))
+    substrate = substrates.mesh(vertices, faces, init_pos="intra", periodic=True, quiet=True)
+    signals, pos = simulations.simulation(n_s, D, gradient, dt, substrate, final_pos=True, quiet=True)
+    assert np.all(np.max(pos, axis=0) < substrate.voxel_size)
+    assert np.all(np.min(pos, axis=0) > 0)
+    ref = O.simulation(n_s, D, gradient, dt, substrate, seed=123, n_threads=8)
+    assert np.array_equal(pos, ref["positions"])
+    assert np.allclose(signals, ref["signals"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name,periodic,init_pos,dt", [
+    ("example_mesh", False, "uniform", 1e-4),
+    ("example_mesh", True, "uniform", 1e-2),
+    ("fibre_mesh", True, "uniform", 1e-3),
+    ("fibre_mesh", False, "uniform", 1e-2),
+    ("neuron_model", False, "extra", 1e-3),
+])
+def test_real_meshes_match_oracle(name, periodic, init_pos, dt):
+    """The other irregular meshes the reference ships (example_mesh.pkl, fibre_mesh.pkl), and the
+    neuron model closed by walls with walkers outside it: positions bit for bit against the oracle,
+    short and long steps, two measurements."""
+    from disimpy_b200 import simulations, substrates
+    from oracle import oracle as O
+    vertices, faces = _real_mesh(name)
+    gradient = np.ones((2, 60, 3)) * np.array([1.0, 0.5])[:, None, None]
+    substrate = substrates.mesh(vertices, faces, periodic, init_pos=init_pos, quiet=True,
+                                n_sv=np.array([20, 20, 20]))
+    n_s = 2000
+    signals, pos = simulations.simulation(n_s, D, gradient, dt, substrate, final_pos=True, quiet=True, seed=5)
+    ref = O.simulation(n_s, D, gradient, dt, substrate, seed=5, n_threads=8)
+    assert np.array_equal(pos, ref["positions"])
+    assert np.allclose(signals, ref["signals"], rtol=1e-12, atol=0)
+    if not periodic:
+        assert np.all(pos > 0) and np.all(pos < substrate.voxel_size)
+
+
+def test_fill_mesh_sphere():  # test_simulations.py:428-456 (test__fill_mesh)
+    from disimpy_b200 import simulations, substrates
+    meshes = load_golden("ref_meshes")
+    vertices, faces = meshes["sphere_mesh_vertices"], meshes["sphere_mesh_faces"]
+    n_s = int(1e4)
+    for n_sv in [np.array([1, 1, 1]), np.array([1, 5, 20]), np.array([10, 10, 10])]:
+        for periodic in [True, False]:
+            for padding in [np.zeros(3), np.zeros(3) + 1e-6]:
+                substrate = substrates.mesh(vertices, faces, periodic, padding=padding, n_sv=n_sv, quiet=True)
+                points = simulations._fill_mesh(n_s, substrate, True, seed=123)
+                r = (substrate.voxel_size - padding * 2) / 2
+                points -= r + padding
+                assert np.max(np.linalg.norm(points, axis=1)) < np.min(r)
+                npt.assert_almost_equal(np.mean(points, axis=0), np.zeros(3))
+                points = simulations._fill_mesh(n_s, substrate, False, seed=123)
+                points -= r + padding
+                assert np.min(np.linalg.norm(points, axis=1)) > 0.9 * np.min(r)
+                npt.assert_almost_equal(np.mean(points, axis=0), np.zeros(3))

@@ -12,7 +12,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden, oracle_substrate, product_substrate
+from conftest import GOLDEN, ROOT, load_golden, oracle_substrate, product_substrate
 
 
 def test_library_exports_every_declared_symbol():
@@ -449,3 +449,27 @@ def test_tools_and_entry_points_compile():
     assert len(files) > 5
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+def test_gradient_helpers_bit_equal_to_reference(tmp_path):
+    """pgse / set_b / calc_b / calc_q / interpolate_gradient return the reference's arrays bit for bit
+    (tests/golden/ref_gradients.npz: outputs of disimpy/gradients.py on fixed inputs), so a script
+    ported to this package feeds the walk the same gradient samples."""
+    from disimpy_b200 import gradients
+    r = np.load(os.path.join(GOLDEN, "ref_gradients.npz"))
+    g, dt = gradients.pgse(5e-3, 20e-3, 37, r["bvals"], r["bvecs"])
+    assert np.array_equal(g, r["pgse"]) and dt == float(r["pgse_dt"])
+    assert np.array_equal(gradients.calc_b(r["w"], 1e-3), r["calc_b"])
+    assert np.array_equal(gradients.calc_q(r["w"], 1e-3), r["calc_q"])
+    assert np.array_equal(gradients.set_b(r["w"], 1e-3, np.arange(1, 6) * 1e9), r["set_b"])
+    g, dt = gradients.interpolate_gradient(r["w"], 1e-3, 93)
+    assert np.array_equal(g, r["interp"]) and dt == float(r["interp_dt"])
+    # Camino scheme files (disimpy/gradients.py:182-212)
+    path = tmp_path / "scheme.txt"
+    rows = np.hstack([np.full((3, 1), 4.0), np.full((3, 1), 2e-3), np.arange(36.0).reshape(3, 12)])
+    path.write_text("VERSION: GRADIENT_WAVEFORM\n" + "\n".join(" ".join(repr(float(x)) for x in row) for row in rows) + "\n")
+    g, dt = gradients.load_camino_scheme_file(str(path))
+    assert g.shape == (3, 4, 3) and dt == 2e-3 and np.array_equal(g.ravel(), np.arange(36.0))
+    path.write_text("VERSION: 1\n")
+    with pytest.raises(Exception):
+        gradients.load_camino_scheme_file(str(path))
