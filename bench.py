@@ -165,6 +165,8 @@ def secondary_workloads(device, fp64_peak, sm_mhz):
                                utils.vec2vec_rotmat(np.array([1.0, 0, 0]), np.array([1.0, 1.0, 1.0])))
     cyl = substrates.cylinder(5e-6, np.array([0.0, 0.0, 1.0]))
     cases = [
+        ("free diffusion (BASELINE config 1 on the GPU at 1e6 walkers), 1e6 walkers x 1000 steps, 1 measurement",
+         substrates.free(), g1k, dt1k, 1_000_000),
         ("cylinder r=5um, 1e6 walkers x %d steps, 1 measurement" % N_T, cyl, g1e4, dt1e4, 1_000_000),
         ("sphere r=10um, 1e6 walkers x 1000 steps, 180 measurements", substrates.sphere(RADIUS), g180, dt180, 1_000_000),
         ("ellipsoid 10x5x2.5um rotated, 1e6 walkers x 1000 steps, 60 directions x 3 shells", ell, g180, dt180, 1_000_000),
@@ -181,6 +183,8 @@ def secondary_workloads(device, fp64_peak, sm_mhz):
             pos = simulations._initial_positions_cylinder(n, sub.radius, np.eye(3), SEED)
         elif sub.type == "ellipsoid":
             pos = simulations._initial_positions_ellipsoid(n, sub.semiaxes, sub.R, SEED)
+        elif sub.type == "free":
+            pos = np.zeros((n, 3))
         else:
             if mesh_pos is None:
                 mesh_pos = simulations._fill_mesh(n, sub, False, SEED)
@@ -245,31 +249,85 @@ def secondary_workloads(device, fp64_peak, sm_mhz):
     return out
 
 
-def config5_shard():
-    """BASELINE config 5 as one GPU sees it: the 1 048 576-triangle periodic mesh, 180 waveforms,
-    1000 steps and the 1.25e7 walkers a rank of the 8-GPU job holds, through simulation() (mesh
-    upload, initial positions drawn on the GPU, walk, signal back).  The whole job is this on
-    every rank (profiles/r01_k_config5.json has the 2- and 8-GPU runs)."""
+def mesh_e2e_all_ranks(world, rank, dist, torch):
+    """BASELINE configs 4 and 5 through the public simulation() call on EVERY rank of the run (weak
+    scaling: 1e6, resp. 1.25e7 walkers per GPU -- at 8 GPUs the latter is the whole 1e8-walker job of
+    config 5): mesh upload, the sharded mesh sampler with its all-gather, walk, the one all-reduce.
+    Time = max over ranks of the wall time per call, barriers on both sides."""
     from disimpy_b200 import gradients, meshgen, simulations, substrates
     dirs = meshgen.fibonacci_sphere(60)
-    g, dt = gradients.pgse(10e-3, 30e-3, 1000, [1e9] * 60 + [2e9] * 60 + [3e9] * 60, np.vstack([dirs, dirs, dirs]))
-    v, f, pad, _ = meshgen.tube_lattice(16, 16, 5e-6, 12e-6, 40e-6, 128, 16)
-    t0 = time.perf_counter()
-    sub = substrates.mesh(v, f, True, padding=pad, init_pos="extra", n_sv=np.array([100, 100, 50]), quiet=True)
-    mesh_s = time.perf_counter() - t0
-    n = 12_500_000
-    simulations.simulation(100_000, DIFFUSIVITY, g, dt, sub, seed=SEED, quiet=True)
-    best = None
-    for _ in range(2):
-        t0 = time.perf_counter()
-        sig = simulations.simulation(n, DIFFUSIVITY, g, dt, sub, seed=SEED, quiet=True)
-        e2e_s = time.perf_counter() - t0
-        best = e2e_s if best is None else min(best, e2e_s)
-    return {"workload": "BASELINE config 5, one GPU's share of the 8-GPU job: periodic mesh of 16x16 tubes (%d triangles, "
-                        "n_sv 100x100x50), init_pos extra, %d walkers x 1000 steps x 180 waveforms, through simulation()"
-                        % (len(f), n),
-            "value": n * g.shape[1] / best, "unit": UNIT, "e2e_ms": 1e3 * best,
-            "substrates_mesh_ms": 1e3 * mesh_s, "signal0_over_n": float(sig[0]) / n}
+    g180, dt180 = gradients.pgse(10e-3, 30e-3, 1000, [1e9] * 60 + [2e9] * 60 + [3e9] * 60, np.vstack([dirs, dirs, dirs]))
+    g1, dt1 = gradients.pgse(10e-3, 30e-3, 1000, [1e9], [[1.0, 0.0, 0.0]])
+    out = []
+    specs = [
+        ("config4", "periodic mesh of 8x8 tubes (98304 triangles, n_sv 50^3), init_pos extra, %d walkers per GPU x 1000 steps, "
+                    "1 measurement", (8, 8, 64, 12), [50, 50, 50], 1_000_000, g1, dt1),
+        ("config5", "periodic mesh of 16x16 tubes (1048576 triangles, n_sv 100x100x50), init_pos extra, %d walkers per GPU x "
+                    "1000 steps x 180 waveforms", (16, 16, 128, 16), [100, 100, 50], 12_500_000, g180, dt180),
+    ]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for key, name, (nx, ny, n_theta, n_z), n_sv, per_gpu, g, dt in specs:
+        try:
+            v, f, pad, _ = meshgen.tube_lattice(nx, ny, 5e-6, 12e-6, 40e-6, n_theta, n_z)
+            t0 = time.perf_counter()
+            sub = substrates.mesh(v, f, True, padding=pad, init_pos="extra", n_sv=np.array(n_sv), quiet=True)
+            mesh_s = time.perf_counter() - t0
+            n = per_gpu * world
+            simulations.simulation(max(100_000, 2048 * world), DIFFUSIVITY, g, dt, sub, seed=SEED, quiet=True)   # warm-up
+            times = []
+            for _ in range(2):
+                barrier()
+                t0 = time.perf_counter()
+                sig = simulations.simulation(n, DIFFUSIVITY, g, dt, sub, seed=SEED, quiet=True)
+                barrier()
+                times.append(time.perf_counter() - t0)
+            te = torch.tensor(times, dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            best = float(te.min().cpu())
+            out.append({"config": key, "workload": name % per_gpu, "walkers_total": n, "n_gpus": world,
+                        "value": n * g.shape[1] / best, "unit": UNIT, "e2e_ms": 1e3 * best,
+                        "per_gpu_value": per_gpu * g.shape[1] / best, "substrates_mesh_ms": 1e3 * mesh_s,
+                        "signal0_over_n": float(np.asarray(sig)[0]) / n,
+                        "measured": "simulation() end to end on every rank (mesh upload, initial positions drawn on the "
+                                    "GPUs, walk, all-reduce), max over ranks, best of 2"})
+        except Exception as e:  # never let a secondary workload cost the bench line
+            out.append({"config": key, "error": repr(e)})
+    return out
+
+
+def reference_baselines():
+    """The unmodified reference timed beside the product in the same run (north_star: "reported next
+    to the reference's Numba-CUDA path on the same B200 and its NUMBA_ENABLE_CUDASIM CPU path timed on
+    the host cores, with core count stated"): tools/bench_reference_gpu.py and
+    tools/bench_reference_cudasim.py as subprocesses (they import the reference from oracle/_ref, a
+    git-ignored pip install of it; test infrastructure, never the product).  Reported baselines,
+    not targets."""
+    out = {}
+    for key, cmd, limit in (
+            ("numba_cuda", [sys.executable, os.path.join(ROOT, "tools", "bench_reference_gpu.py"), "--json"], 420),
+            ("cudasim", [sys.executable, os.path.join(ROOT, "tools", "bench_reference_cudasim.py"), "128", "50", "--json"], 300)):
+        if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "disimpy")):
+            out[key] = {"unavailable": "oracle/_ref (pip install --target of the reference) is not present"}
+            continue
+        try:
+            t0 = time.perf_counter()
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=limit)
+            line = [l for l in res.stdout.splitlines() if l.startswith("{")]
+            if res.returncode != 0 or not line:
+                out[key] = {"unavailable": "rc %d: %s" % (res.returncode, (res.stderr or res.stdout)[-300:])}
+            else:
+                out[key] = json.loads(line[-1])
+                out[key]["seconds_spent"] = time.perf_counter() - t0
+        except Exception as e:
+            out[key] = {"unavailable": repr(e)}
+    return out
 
 
 def run_reference(args, rank):
@@ -315,6 +373,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-mesh", action="store_true", help="skip the mesh workloads (configs 4 and 5) through simulation()")
+    ap.add_argument("--no-reference-baselines", action="store_true",
+                    help="skip timing the unmodified reference (Numba-CUDA on this GPU, CUDASIM on the host)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
 
@@ -364,12 +425,12 @@ def main():
     def one_step():
         walk.set_positions_dev(d_pos0.data_ptr())
         walk.run(0, N_T)
-        sig, n_valid = walk.signal()          # syncs the library's stream, 16 bytes D2H
         if world > 1:
-            sig_buf.copy_(torch.tensor([sig[0], float(n_valid)], dtype=torch.float64))
-            dist.all_reduce(sig_buf)          # the one collective of the path (NCCL)
-            out = sig_buf.cpu().numpy()
-            return out[0], int(out[1])
+            walk.copy_signal_to(sig_buf.data_ptr())   # waits for the walk; (sum cos, valid count) stay on the device
+            dist.all_reduce(sig_buf)                  # the one collective of the path (NCCL)
+            out = sig_buf.cpu().numpy()               # 16 bytes D2H
+            return out[0], int(round(out[1]))
+        sig, n_valid = walk.signal()          # syncs the library's stream, 16 bytes D2H
         return sig[0], n_valid
 
     def barrier():
@@ -430,8 +491,9 @@ def main():
                             "frac": fp64_counted * (hi - lo) * N_T / (kernel_ms * 1e-3) / peak.value,
                             "reference_work_per_walker_step": per_step},
         "traffic_bytes_per_launch_ncu": NCU_DRAM_BYTES_PER_LAUNCH,
-        "peak_source": "measured live by dsb_measure_fp64_peak (independent DFMA chains); "
-                       "MEASURED_PEAKS.json has no FP64 figure",
+        "peak_source": "REPO-MEASURED, not driver-measured: dsb_measure_fp64_peak runs independent DFMA chains on every SM "
+                       "in this process right after the timed region (same clocks); MEASURED_PEAKS.json (driver-written) "
+                       "has no FP64 figure.  148 SMs x 64 FP64 lanes x 1.965 GHz = 18.6 T instr/s is the nominal ceiling",
         "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": hbm_peak,
                 "frac": hbm_achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
@@ -458,16 +520,48 @@ def main():
                "d2h_bytes_per_step": 16, "ms_per_step": 1e3 * e2e_s,
                "signal": float(np.asarray(sig_e2e)[0])}
 
+    # the mesh configurations (BASELINE configs 4 and 5) through simulation() on every rank
+    mesh = None
+    if not args.no_mesh:
+        mesh = mesh_e2e_all_ranks(world, rank, dist if world > 1 else None, torch)
+
+    # the default call of the public API shows progress (quiet=False): a handful of launches
+    # instead of the part-by-part pipeline; timed once so that the path users hit first is on record
+    verbose_e2e = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            t0 = time.perf_counter()
+            simulations.simulation(n_global, DIFFUSIVITY, g, dt, sub, seed=SEED)
+            verbose_e2e = {"value": units_per_step / (time.perf_counter() - t0), "unit": UNIT,
+                           "note": "simulation(..., quiet=False): positions drawn first, ~20 launches with progress output"}
+
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base, _ = cpu_baseline(sub, g, dt)
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
         secondary = secondary_workloads(local_rank, peak.value, (clocks or {}).get("sm_mhz"))
-        try:
-            secondary.append(config5_shard())
-        except Exception as e:  # never let the extra workload cost the bench line
-            secondary.append({"workload": "BASELINE config 5 shard", "error": repr(e)})
+    baselines = None
+    if rank == 0 and world == 1 and not args.no_reference_baselines:
+        walk.close()                 # give the device memory back before another process uses the GPU
+        _lib.lib().dsb_release_cache()
+        baselines = reference_baselines()
+        nb = baselines.get("numba_cuda", {})
+        if "sphere_1e6x1e4_kernel_only" in nb:
+            ratios = {"sphere_kernel": value / nb["sphere_1e6x1e4_kernel_only"]["walker_steps_per_s"]}
+            if e2e:
+                ratios["sphere_e2e"] = e2e["value"] / nb["sphere_1e6x1e4_e2e"]["walker_steps_per_s"]
+            m4 = next((w for w in (secondary or []) if w.get("workload", "").startswith("periodic mesh")), None)
+            if m4 and "mesh_98k_1e6x1e3_kernel_only" in nb:
+                ratios["mesh_kernel"] = m4["value"] / nb["mesh_98k_1e6x1e3_kernel_only"]["walker_steps_per_s"]
+            baselines["ratio_this_repo_over_numba_cuda"] = ratios
+        cs = baselines.get("cudasim", {})
+        if "free" in cs:
+            free = next((w for w in (secondary or []) if w.get("workload", "").startswith("free diffusion")), None)
+            if free:
+                baselines["ratio_this_repo_over_cudasim_free"] = free["value"] / cs["free"]["walker_steps_per_s"]
 
     if rank == 0:
         line = {
@@ -482,7 +576,8 @@ def main():
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
             "signal": float(signal), "n_valid": int(n_valid),
-            "other_workloads": secondary,
+            "mesh": mesh, "e2e_default_verbose_call": verbose_e2e,
+            "other_workloads": secondary, "baselines": baselines,
         }
         sys.stdout.flush()
         os.write(result_fd, (json.dumps(line) + "\n").encode())

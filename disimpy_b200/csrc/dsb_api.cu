@@ -17,14 +17,41 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace {
 
 thread_local std::string g_err;
+
+// NVTX range around every phase of a call (upload, RNG init, walk, reduction, read-back): shows up
+// in nsys / ncu timelines, costs nothing when no tool is attached.
+struct Range {
+    explicit Range(const char *name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range &) = delete;
+    Range &operator=(const Range &) = delete;
+};
 
 int fail(int code, const std::string &msg)
 {
     g_err = msg;
     return code;
+}
+
+// Nothing may throw across the C boundary: entry points that allocate host memory run their body
+// through this.
+template <typename Fn>
+int guarded(Fn fn)
+{
+    try {
+        return fn();
+    } catch (const std::bad_alloc &) {
+        return fail(DSB_ENOMEM, "host allocation failed");
+    } catch (const std::exception &e) {
+        return fail(DSB_EINVAL, std::string("unexpected exception: ") + e.what());
+    } catch (...) {
+        return fail(DSB_EINVAL, "unexpected exception");
+    }
 }
 
 #define DSB_CUDA(expr)                                                                            \
@@ -148,12 +175,23 @@ int launch_rng_init(int device, uint64_t seed, uint64_t start, int64_t n, ulongl
 // cudaMalloc / cudaFree synchronise the device and cost from a few to tens of milliseconds per
 // simulation() call (more when another allocator holds most of the memory), so buffers of
 // destroyed handles are kept per device and size and handed to the next handle.
+size_t cache_cap_from_env(size_t dflt, size_t divisor)
+{
+    const char *e = getenv("DISIMPY_B200_CACHE_MB");
+    if (!e || !*e) return dflt;
+    char *end = nullptr;
+    const unsigned long long mb = strtoull(e, &end, 10);
+    if (end == e) return dflt;
+    return (size_t)mb * (size_t(1) << 20) / divisor;
+}
+
 struct BufferCache {
     std::mutex mu;
     std::multimap<std::pair<int, size_t>, void *> idle;
     std::map<void *, std::pair<int, size_t>> live;
     size_t idle_bytes = 0;
-    static constexpr size_t kMaxIdleBytes = size_t(16) << 30;
+    // idle device memory kept for the next handle; DISIMPY_B200_CACHE_MB overrides (0: keep nothing)
+    size_t max_idle_bytes = cache_cap_from_env(size_t(16) << 30, 1);
 } g_cache;
 
 cudaError_t cache_malloc(void **out, size_t bytes)
@@ -196,7 +234,7 @@ void cache_free(void *p)
     }
     const std::pair<int, size_t> key = it->second;
     g_cache.live.erase(it);
-    if (g_cache.idle_bytes + key.second > BufferCache::kMaxIdleBytes) {
+    if (g_cache.idle_bytes + key.second > g_cache.max_idle_bytes) {
         cudaFree(p);
         return;
     }
@@ -221,7 +259,7 @@ struct HostCache {
     std::multimap<size_t, void *> idle;
     std::map<void *, size_t> live;
     size_t idle_bytes = 0;
-    static constexpr size_t kMaxIdleBytes = size_t(4) << 30;
+    size_t max_idle_bytes = cache_cap_from_env(size_t(4) << 30, 4);  // a quarter of the device cap
 } g_host_cache;
 
 void *host_cache_malloc(size_t bytes)
@@ -259,7 +297,7 @@ void host_cache_free(void *p)
     }
     const size_t bytes = it->second;
     g_host_cache.live.erase(it);
-    if (g_host_cache.idle_bytes + bytes > HostCache::kMaxIdleBytes) {
+    if (g_host_cache.idle_bytes + bytes > g_host_cache.max_idle_bytes) {
         cudaFreeHost(p);
         return;
     }
@@ -354,6 +392,7 @@ struct MeshBuffers {
 // record per triangle holding A, B-A, C-A (72 bytes) and a pad, read with five 128-bit loads.
 int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
 {
+    Range nvtx("dsb: mesh re-layout + upload");
     if (!m.vertices || !m.faces || !m.xs || !m.ys || !m.zs || !m.subvoxel_indices ||
         (m.n_triangle_indices > 0 && !m.triangle_indices))
         return fail(DSB_EINVAL, "mesh: null array");
@@ -503,6 +542,7 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
 int build_fill_columns(MeshBuffers &mb)
 {
     if (mb.columns.entry) return DSB_OK;
+    Range nvtx("dsb: sampler column lists");
     const int64_t n0 = mb.n_sv[0], n1 = mb.n_sv[1], n2 = mb.n_sv[2];
     const int64_t n_cols = n1 * n2;
     std::vector<int> start((size_t)n_cols + 1), cnt((size_t)(n_cols * n0));
@@ -616,17 +656,6 @@ constexpr size_t many_meas_smem()
 template <int SUB, int MAXC>
 void launch_walk_cells(const dsb::KParams &kp, int grid, cudaStream_t st)
 {
-#ifdef DSB_TWO_WALKERS
-    if constexpr (SUB >= 1 && SUB <= 3) {   // experiment: two walkers per lane (dsb_kernels.cuh)
-        switch (kp.n_meas <= dsb::kMaxRegMeas ? kp.n_meas : 0) {
-        case 1: dsb::walk2_kernel<SUB, 1><<<grid, dsb::kBlock / 2, 0, st>>>(kp); return;
-        case 2: dsb::walk2_kernel<SUB, 2><<<grid, dsb::kBlock / 2, 0, st>>>(kp); return;
-        case 3: dsb::walk2_kernel<SUB, 3><<<grid, dsb::kBlock / 2, 0, st>>>(kp); return;
-        case 4: dsb::walk2_kernel<SUB, 4><<<grid, dsb::kBlock / 2, 0, st>>>(kp); return;
-        default: break;
-        }
-    }
-#endif
     switch (kp.n_meas <= dsb::kMaxRegMeas ? kp.n_meas : 0) {
     case 1: dsb::walk_kernel<SUB, 1, MAXC><<<grid, dsb::kBlock, 0, st>>>(kp); break;
     case 2: dsb::walk_kernel<SUB, 2, MAXC><<<grid, dsb::kBlock, 0, st>>>(kp); break;
@@ -840,8 +869,10 @@ int dsb_destroy(dsb_sim *s)
     return DSB_OK;
 }
 
-int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
+// *live follows the handle while it is being built, so that dsb_create can free it if anything throws
+static int create_impl(const dsb_params *params, const double *gradient, dsb_sim **out, dsb_sim **live)
 {
+    Range nvtx("dsb_create: buffers + gradient upload + RNG init");
     if (!out) return fail(DSB_EINVAL, "null out pointer");
     *out = nullptr;
     int rc = check_params(params, gradient);
@@ -852,6 +883,7 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
     DSB_CUDA(cudaSetDevice(params->device));
     dsb_sim *s = new (std::nothrow) dsb_sim();
     if (!s) return fail(DSB_ENOMEM, "host allocation failed");
+    *live = s;
     s->prm = *params;
     const int64_t N = params->n_walkers, M = params->n_meas, T = params->n_t;
     s->grid = (int)((N + dsb::kBlock - 1) / dsb::kBlock);
@@ -862,7 +894,7 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
             std::string msg = std::string(#expr) + ": " + cudaGetErrorString(e_); \
             int code = e_ == cudaErrorMemoryAllocation ? DSB_ENOMEM : DSB_ECUDA;  \
             cudaGetLastError();       \
-            dsb_destroy(s);           \
+            dsb_destroy(s), *live = nullptr;           \
             return fail(code, msg);   \
         }                             \
     } while (0)
@@ -915,7 +947,7 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
         rc = upload_mesh(params->mesh, s->mesh);
         if (rc) {
             std::string keep = g_err;
-            dsb_destroy(s);
+            dsb_destroy(s), *live = nullptr;
             return fail(rc, keep);
         }
     }
@@ -924,11 +956,24 @@ int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
                          reinterpret_cast<ulonglong2 *>(s->d_rng0), s->stream);
     if (rc) {
         std::string keep = g_err;
-        dsb_destroy(s);
+        dsb_destroy(s), *live = nullptr;
         return fail(rc, keep);
     }
     *out = s;
+    *live = nullptr;
     return DSB_OK;
+}
+
+int dsb_create(const dsb_params *params, const double *gradient, dsb_sim **out)
+{
+    dsb_sim *live = nullptr;
+    const int rc = guarded([&] { return create_impl(params, gradient, out, &live); });
+    if (live) {  // an exception left a half-built handle behind
+        std::string keep = g_err;
+        dsb_destroy(live);
+        g_err = keep;
+    }
+    return rc;
 }
 
 static int rewind_sim(dsb_sim *s)
@@ -954,6 +999,7 @@ static int rewind_sim(dsb_sim *s)
 int dsb_set_positions(dsb_sim *s, const double *positions)
 {
     if (!s || !positions) return fail(DSB_EINVAL, "null argument");
+    Range nvtx("dsb_set_positions: H2D");
     DSB_CUDA(cudaSetDevice(s->prm.device));
     DSB_CUDA(cudaMemcpyAsync(s->d_pos, positions, sizeof(double) * 3 * s->prm.n_walkers, cudaMemcpyHostToDevice, s->stream));
     return rewind_sim(s);
@@ -1048,6 +1094,7 @@ int dsb_run(dsb_sim *s, int64_t t0, int64_t t1)
     if (s->t_cur < 0) return fail(DSB_ESTATE, "dsb_run before dsb_set_positions");
     if (s->parts_done > 0) return fail(DSB_ESTATE, "dsb_run after dsb_run_part: finish the run part by part");
     if (t0 != s->t_cur || t1 <= t0 || t1 > s->prm.n_t) return fail(DSB_EINVAL, "bad step range");
+    Range nvtx("dsb_run: walk (+ signal reduction)");
     DSB_CUDA(cudaSetDevice(s->prm.device));
     int rc = launch_walk_range(s, s->stream, 0, s->prm.n_walkers, t0, t1);
     if (rc) return rc;
@@ -1094,6 +1141,7 @@ int dsb_run_part(dsb_sim *s, int64_t w0, int64_t w1)
     if (s->t_cur != 0) return fail(DSB_ESTATE, "dsb_run_part needs a rewound handle (dsb_rewind)");
     if (w0 < 0 || w1 <= w0 || w1 > s->prm.n_walkers || w0 % dsb::kBlock != 0)
         return fail(DSB_EINVAL, "bad walker range (w0 must be a multiple of 128)");
+    Range nvtx("dsb_run_part: walk");
     DSB_CUDA(cudaSetDevice(s->prm.device));
     cudaStream_t st = s->part_parity ? s->stream2 : s->stream;
     if (s->part_parity) DSB_CUDA(cudaStreamWaitEvent(st, s->ev_rewind, 0));
@@ -1130,15 +1178,18 @@ int dsb_sync(dsb_sim *s)
 
 int dsb_get_signal(dsb_sim *s, double *signal, int64_t *n_valid)
 {
-    if (!s || !signal) return fail(DSB_EINVAL, "null argument");
-    if (!s->finalized) return fail(DSB_ESTATE, "signal is available after the last time step only");
-    DSB_CUDA(cudaSetDevice(s->prm.device));
-    std::vector<double> h((size_t)s->prm.n_meas + 1);
-    DSB_CUDA(cudaMemcpyAsync(h.data(), s->d_signal, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    DSB_CUDA(cudaStreamSynchronize(s->stream));
-    memcpy(signal, h.data(), sizeof(double) * (size_t)s->prm.n_meas);
-    if (n_valid) *n_valid = (int64_t)llround(h.back());
-    return DSB_OK;
+    return guarded([&]() -> int {
+        if (!s || !signal) return fail(DSB_EINVAL, "null argument");
+        if (!s->finalized) return fail(DSB_ESTATE, "signal is available after the last time step only");
+        Range nvtx("dsb_get_signal: wait + D2H");
+        DSB_CUDA(cudaSetDevice(s->prm.device));
+        std::vector<double> h((size_t)s->prm.n_meas + 1);
+        DSB_CUDA(cudaMemcpyAsync(h.data(), s->d_signal, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        DSB_CUDA(cudaStreamSynchronize(s->stream));
+        memcpy(signal, h.data(), sizeof(double) * (size_t)s->prm.n_meas);
+        if (n_valid) *n_valid = (int64_t)llround(h.back());
+        return DSB_OK;
+    });
 }
 
 #define DSB_GETTER(name, type, member, count)                                                             \
@@ -1258,17 +1309,19 @@ int dsb_protocol_rank(dsb_sim *s) { return s ? s->rank : 0; }
 int dsb_protocol_factor(const double *gradient, int64_t n_meas, int64_t n_t, int32_t max_rank, int32_t *rank, double *u,
                         double *v)
 {
-    if (!gradient || !rank || !u || !v || n_meas <= 0 || n_t <= 0 || max_rank <= 0) return fail(DSB_EINVAL, "bad arguments");
-    std::vector<double> U, V;
-    int r = 0;
-    if (!factor_low_rank(gradient, n_meas, 3 * n_t, max_rank, U, V, r)) {
-        *rank = 0;
+    return guarded([&]() -> int {
+        if (!gradient || !rank || !u || !v || n_meas <= 0 || n_t <= 0 || max_rank <= 0) return fail(DSB_EINVAL, "bad arguments");
+        std::vector<double> U, V;
+        int r = 0;
+        if (!factor_low_rank(gradient, n_meas, 3 * n_t, max_rank, U, V, r)) {
+            *rank = 0;
+            return DSB_OK;
+        }
+        *rank = r;
+        std::copy(U.begin(), U.end(), u);
+        std::copy(V.begin(), V.end(), v);
         return DSB_OK;
-    }
-    *rank = r;
-    std::copy(U.begin(), U.end(), u);
-    std::copy(V.begin(), V.end(), v);
-    return DSB_OK;
+    });
 }
 void *dsb_stream(dsb_sim *s) { return s ? (void *)s->stream : nullptr; }
 double *dsb_signal_dev(dsb_sim *s) { return s ? s->d_signal : nullptr; }
@@ -1315,6 +1368,7 @@ int dsb_fill_mesh_sim(dsb_sim *s, const double *voxel_size, int intra, uint64_t 
     if (!s || !voxel_size || n_points <= 0 || cuda_bs <= 0 || first < 0) return fail(DSB_EINVAL, "bad arguments");
     if (s->prm.substrate != DSB_MESH) return fail(DSB_ESTATE, "dsb_fill_mesh_sim needs a mesh handle");
     if (first + s->prm.n_walkers > n_points || n_points > 0x7fffffffLL) return fail(DSB_EINVAL, "bad point range");
+    Range nvtx("dsb_fill_mesh_sim: initial positions on the GPU");
     DSB_CUDA(cudaSetDevice(s->prm.device));
     const int64_t n_states = (n_points + cuda_bs - 1) / cuda_bs * cuda_bs;
     const int n_blocks = (int)((n_points + dsb::kCompactBlock - 1) / dsb::kCompactBlock);
@@ -1439,55 +1493,204 @@ int dsb_fill_shard_round(dsb_sim *s, const double *voxel_size, int intra, double
 int dsb_fill_mesh(int32_t device, const dsb_mesh *mesh, const double *voxel_size, int intra, uint64_t seed,
                   int64_t n_points, int64_t cuda_bs, double *points)
 {
-    if (!mesh || !voxel_size || !points || n_points <= 0 || cuda_bs <= 0) return fail(DSB_EINVAL, "bad arguments");
-    DSB_CUDA(cudaSetDevice(device));
-    MeshBuffers mb;
-    int rc = upload_mesh(*mesh, mb);
-    if (rc) {
+    return guarded([&]() -> int {
+        if (!mesh || !voxel_size || !points || n_points <= 0 || cuda_bs <= 0) return fail(DSB_EINVAL, "bad arguments");
+        DSB_CUDA(cudaSetDevice(device));
+        MeshBuffers mb;
+        int rc = upload_mesh(*mesh, mb);
+        if (rc) {
+            mb.release();
+            return rc;
+        }
+        const int64_t n_states = (n_points + cuda_bs - 1) / cuda_bs * cuda_bs;
+        ulonglong2 *d_rng = nullptr;
+        double *d_pts = nullptr;
+        int *d_count = nullptr;
+        cudaError_t e = cudaMalloc(&d_rng, sizeof(ulonglong2) * (size_t)n_states);
+        if (e == cudaSuccess) e = cudaMalloc(&d_pts, sizeof(double) * 3 * (size_t)n_points);
+        if (e == cudaSuccess) e = cudaMalloc(&d_count, sizeof(int));
+        if (e != cudaSuccess) rc = fail(DSB_ENOMEM, cudaGetErrorString(e));
+        if (!rc) rc = build_fill_columns(mb);
+        if (!rc) rc = launch_rng_init(device, seed, 0, n_states, d_rng, 0);
+        std::vector<double> round_pts((size_t)n_points * 3);
+        int64_t have = 0;
+        const double inf = INFINITY;
+        // The reference launches one round per host-loop iteration, keeps the accepted points of
+        // every round in thread order and stops once it has enough (simulations.py:554-579).
+        for (int round = 0; !rc && have < n_points; ++round) {
+            if (round > 100000) {
+                rc = fail(DSB_ESTATE, "fill_mesh: no acceptable points (is the surface closed?)");
+                break;
+            }
+            dsb::fill_mesh_kernel<<<(unsigned)((n_points + 127) / 128), 128>>>(mb.dev, mb.columns, voxel_size[0], voxel_size[1],
+                                                                                voxel_size[2], intra, (long long)n_points,
+                                                                                d_rng, d_pts);
+            e = cudaGetLastError();
+            if (e == cudaSuccess)
+                e = cudaMemcpy(round_pts.data(), d_pts, sizeof(double) * 3 * (size_t)n_points, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) {
+                rc = fail(DSB_ECUDA, cudaGetErrorString(e));
+                break;
+            }
+            for (int64_t i = 0; i < n_points && have < n_points; ++i)
+                if (round_pts[3 * i] != inf) {
+                    memcpy(points + 3 * have, &round_pts[3 * i], 3 * sizeof(double));
+                    ++have;
+                }
+        }
+        cudaFree(d_rng);
+        cudaFree(d_pts);
+        cudaFree(d_count);
         mb.release();
         return rc;
-    }
-    const int64_t n_states = (n_points + cuda_bs - 1) / cuda_bs * cuda_bs;
-    ulonglong2 *d_rng = nullptr;
-    double *d_pts = nullptr;
-    int *d_count = nullptr;
-    cudaError_t e = cudaMalloc(&d_rng, sizeof(ulonglong2) * (size_t)n_states);
-    if (e == cudaSuccess) e = cudaMalloc(&d_pts, sizeof(double) * 3 * (size_t)n_points);
-    if (e == cudaSuccess) e = cudaMalloc(&d_count, sizeof(int));
-    if (e != cudaSuccess) rc = fail(DSB_ENOMEM, cudaGetErrorString(e));
-    if (!rc) rc = build_fill_columns(mb);
-    if (!rc) rc = launch_rng_init(device, seed, 0, n_states, d_rng, 0);
-    std::vector<double> round_pts((size_t)n_points * 3);
-    int64_t have = 0;
-    const double inf = INFINITY;
-    // The reference launches one round per host-loop iteration, keeps the accepted points of
-    // every round in thread order and stops once it has enough (simulations.py:554-579).
-    for (int round = 0; !rc && have < n_points; ++round) {
-        if (round > 100000) {
-            rc = fail(DSB_ESTATE, "fill_mesh: no acceptable points (is the surface closed?)");
-            break;
+    });
+}
+
+int dsb_copy_signal_dev(dsb_sim *s, double *dst_dev)
+{
+    if (!s || !dst_dev) return fail(DSB_EINVAL, "null argument");
+    if (!s->finalized) return fail(DSB_ESTATE, "signal is available after the last time step only");
+    Range nvtx("dsb_copy_signal_dev: wait + D2D");
+    DSB_CUDA(cudaSetDevice(s->prm.device));
+    DSB_CUDA(cudaMemcpyAsync(dst_dev, s->d_signal, sizeof(double) * (size_t)(s->prm.n_meas + 1), cudaMemcpyDeviceToDevice,
+                             s->stream));
+    DSB_CUDA(cudaStreamSynchronize(s->stream));
+    return DSB_OK;
+}
+
+int dsb_fill_mesh_multi(dsb_sim **sims, int32_t n_sims, const double *voxel_size, int intra, uint64_t seed, int64_t n_points)
+{
+    return guarded([&]() -> int {
+        if (!sims || n_sims <= 0 || !voxel_size || n_points <= 0 || n_points > 0x7fffffffLL) return fail(DSB_EINVAL, "bad arguments");
+        Range nvtx("dsb_fill_mesh_multi: sampler rounds over the device list");
+        // handle k holds the global walkers [off_k, off_k + n_k) and evaluates the sampler threads with the
+        // same numbers in every round: together the handles must tile [0, n_points)
+        std::vector<int64_t> w0((size_t)n_sims), w1((size_t)n_sims);
+        int64_t expect = 0;
+        for (int k = 0; k < n_sims; ++k) {
+            if (!sims[k] || sims[k]->prm.substrate != DSB_MESH) return fail(DSB_ESTATE, "dsb_fill_mesh_multi needs mesh handles");
+            w0[(size_t)k] = sims[k]->prm.walker_offset;
+            w1[(size_t)k] = w0[(size_t)k] + sims[k]->prm.n_walkers;
+            if (w0[(size_t)k] != expect) return fail(DSB_EINVAL, "the handles' walker ranges must tile [0, n_points) in order");
+            expect = w1[(size_t)k];
         }
-        dsb::fill_mesh_kernel<<<(unsigned)((n_points + 127) / 128), 128>>>(mb.dev, mb.columns, voxel_size[0], voxel_size[1],
-                                                                            voxel_size[2], intra, (long long)n_points,
-                                                                            d_rng, d_pts);
-        e = cudaGetLastError();
-        if (e == cudaSuccess)
-            e = cudaMemcpy(round_pts.data(), d_pts, sizeof(double) * 3 * (size_t)n_points, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) {
-            rc = fail(DSB_ECUDA, cudaGetErrorString(e));
-            break;
-        }
-        for (int64_t i = 0; i < n_points && have < n_points; ++i)
-            if (round_pts[3 * i] != inf) {
-                memcpy(points + 3 * have, &round_pts[3 * i], 3 * sizeof(double));
-                ++have;
+        if (expect != n_points) return fail(DSB_EINVAL, "the handles' walker ranges must tile [0, n_points) in order");
+        std::vector<double *> accepted((size_t)n_sims, nullptr);
+        std::vector<int64_t> count((size_t)n_sims, 0);
+        std::vector<int> rcs((size_t)n_sims, DSB_OK);
+        std::vector<std::string> errs((size_t)n_sims);
+        auto on_all = [&](auto fn) {   // fn(k) on one host thread per handle; errors collected per handle
+            std::vector<std::thread> pool;
+            for (int k = 0; k < n_sims; ++k)
+                pool.emplace_back([&, k] {
+                    rcs[(size_t)k] = fn(k);
+                    if (rcs[(size_t)k]) errs[(size_t)k] = g_err;
+                });
+            for (auto &th : pool) th.join();
+            for (int k = 0; k < n_sims; ++k)
+                if (rcs[(size_t)k]) return fail(rcs[(size_t)k], errs[(size_t)k]);
+            return (int)DSB_OK;
+        };
+        int rc = on_all([&](int k) -> int {
+            int r = dsb_fill_shard_begin(sims[k], seed, w0[(size_t)k], w1[(size_t)k]);
+            if (r) return r;
+            cudaError_t e = cache_malloc(&accepted[(size_t)k], sizeof(double) * 3 * (size_t)(w1[(size_t)k] - w0[(size_t)k]));
+            return e == cudaSuccess ? DSB_OK : fail(DSB_ENOMEM, cudaGetErrorString(e));
+        });
+        int64_t have = 0;
+        for (int round = 0; !rc && have < n_points; ++round) {
+            if (round > 100000) {
+                rc = fail(DSB_ESTATE, "fill_mesh: no acceptable points (is the surface closed?)");
+                break;
             }
-    }
-    cudaFree(d_rng);
-    cudaFree(d_pts);
-    cudaFree(d_count);
-    mb.release();
-    return rc;
+            rc = on_all([&](int k) { return dsb_fill_shard_round(sims[k], voxel_size, intra, accepted[(size_t)k], &count[(size_t)k]); });
+            if (rc) break;
+            // the round's accepted points, concatenated in handle = thread order, are the global points
+            // have, have + 1, ...: every handle copies its walkers' rows from wherever they were produced
+            rc = on_all([&](int d) -> int {
+                dsb_sim *dst = sims[d];
+                DSB_CUDA(cudaSetDevice(dst->prm.device));
+                int64_t start = have;
+                for (int r = 0; r < n_sims; ++r) {
+                    const int64_t a = std::max(start, w0[(size_t)d]), b = std::min(start + count[(size_t)r], w1[(size_t)d]);
+                    if (a < b)
+                        DSB_CUDA(cudaMemcpyPeerAsync(dst->d_pos + 3 * (a - w0[(size_t)d]), dst->prm.device,
+                                                     accepted[(size_t)r] + 3 * (a - start), sims[r]->prm.device,
+                                                     sizeof(double) * 3 * (size_t)(b - a), dst->stream));
+                    start += count[(size_t)r];
+                }
+                DSB_CUDA(cudaStreamSynchronize(dst->stream));  // the sources are overwritten by the next round
+                return DSB_OK;
+            });
+            for (int k = 0; k < n_sims; ++k) have += count[(size_t)k];
+        }
+        std::string keep = g_err;
+        for (int k = 0; k < n_sims; ++k) {
+            cudaSetDevice(sims[k]->prm.device);
+            cache_free(accepted[(size_t)k]);
+            dsb_fill_shard_end(sims[k]);
+            if (!rc) {
+                int r = rewind_sim(sims[k]);
+                if (r) rc = r, keep = g_err;
+            }
+        }
+        if (rc) g_err = keep;
+        return rc;
+    });
+}
+
+int dsb_simulate_multi(const dsb_params *params, const int32_t *devices, int32_t n_devices, const double *gradient,
+                       const double *positions_in, double *signal_out, int64_t *n_valid_out, double *positions_out,
+                       double *phases_out, uint8_t *iter_exc_out)
+{
+    return guarded([&]() -> int {
+        if (!params || !devices || n_devices <= 0 || !positions_in || !signal_out) return fail(DSB_EINVAL, "null argument");
+        Range nvtx("dsb_simulate_multi");
+        const int64_t N = params->n_walkers, M = params->n_meas;
+        if (N <= 0 || M <= 0) return fail(DSB_EINVAL, "n_walkers and n_meas must be positive");
+        const int n_used = (int)std::min<int64_t>(n_devices, N);   // never an empty shard
+        std::vector<int> rcs((size_t)n_used, DSB_OK);
+        std::vector<std::string> errs((size_t)n_used);
+        std::vector<std::vector<double>> sig((size_t)n_used, std::vector<double>((size_t)M, 0.0));
+        std::vector<int64_t> valid((size_t)n_used, 0);
+        std::vector<std::thread> pool;
+        for (int k = 0; k < n_used; ++k)
+            pool.emplace_back([&, k] {
+                const int64_t lo = N * k / n_used, hi = N * (k + 1) / n_used;
+                dsb_params p = *params;
+                p.device = devices[k];
+                p.n_walkers = hi - lo;
+                p.walker_offset = params->walker_offset + lo;
+                dsb_sim *s = nullptr;
+                int rc = dsb_create(&p, gradient, &s);
+                if (!rc) rc = dsb_set_positions(s, positions_in + 3 * lo);
+                if (!rc) rc = dsb_run(s, 0, p.n_t);
+                if (!rc) rc = dsb_get_signal(s, sig[(size_t)k].data(), &valid[(size_t)k]);
+                if (!rc && positions_out) rc = dsb_get_positions(s, positions_out + 3 * lo);
+                if (!rc && iter_exc_out) rc = dsb_get_iter_exc(s, iter_exc_out + lo);
+                if (!rc && phases_out) {
+                    std::vector<double> ph((size_t)(M * (hi - lo)));
+                    rc = dsb_get_phases(s, ph.data());
+                    if (!rc)
+                        for (int64_t m = 0; m < M; ++m)
+                            memcpy(phases_out + m * N + lo, ph.data() + m * (hi - lo), sizeof(double) * (size_t)(hi - lo));
+                }
+                if (rc) errs[(size_t)k] = g_err;
+                rcs[(size_t)k] = rc;
+                dsb_destroy(s);
+            });
+        for (auto &th : pool) th.join();
+        for (int k = 0; k < n_used; ++k)
+            if (rcs[(size_t)k]) return fail(rcs[(size_t)k], errs[(size_t)k]);
+        int64_t total_valid = 0;
+        for (int64_t m = 0; m < M; ++m) signal_out[m] = 0.0;
+        for (int k = 0; k < n_used; ++k) {   // fixed order: the sum does not depend on which device finished first
+            for (int64_t m = 0; m < M; ++m) signal_out[m] += sig[(size_t)k][(size_t)m];
+            total_valid += valid[(size_t)k];
+        }
+        if (n_valid_out) *n_valid_out = total_valid;
+        return DSB_OK;
+    });
 }
 
 }  // extern "C"

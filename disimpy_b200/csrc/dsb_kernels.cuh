@@ -1128,143 +1128,6 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
     }
 }
 
-// ---------------------------------------------------------------- two walkers per lane (experiment)
-
-#ifdef DSB_TWO_WALKERS
-// EXPERIMENT, not compiled by default (-DDSB_TWO_WALKERS=<parked walkers per warp that trigger a
-// bounce pass>).  Analytic substrates, 1-4 measurements.  A block still owns kBlock
-// walkers but has kBlock / 2 threads: lane l of warp v walks walkers 32 v + l ("A") and
-// kBlock / 2 + 32 v + l ("B").  A walker that hits the wall is parked with its step in flight; the
-// lane goes on stepping its other walker, and once enough of the warp's 64 walkers are parked they
-// are bounced together.  Unlike the one-walker-per-lane batching (ParkFlush) nobody waits for the
-// bounce pass and a lane only idles when both of its walkers are parked.  Every walker executes
-// exactly its own sequence of operations, so trajectories and phases are unchanged; the block's
-// signal partial is summed in a different order than walk_kernel's (last-bit differences).
-template <int MR>
-struct LaneWalker {
-    Vec3 pos;
-    Rng rng;
-    double ph[MR];
-    Flight f;
-    int t;
-    bool live, parked, exc;
-};
-
-template <int SUB, int MR>
-__global__ void __launch_bounds__(kBlock / 2) walk2_kernel(const __grid_constant__ KParams p)
-{
-    static_assert(SUB >= 1 && SUB <= 3 && MR >= 1 && MR <= kMaxRegMeas, "analytic substrates, phases in registers");
-    __shared__ __align__(16) double s_tab[16];
-    if (threadIdx.x < 16) s_tab[threadIdx.x] = __longlong_as_double((long long)c_sincos_tab[threadIdx.x]);
-    __syncthreads();
-
-    const long long N = p.n_walkers;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long w_a = p.w_begin + (long long)blockIdx.x * kBlock + 32 * warp + lane;
-    const long long w_b = w_a + kBlock / 2;
-    auto load = [&](LaneWalker<MR> &x, long long w) {
-        x.live = w < p.w_end;
-        x.parked = false;
-        x.exc = false;
-        x.t = p.t0;
-        x.pos = Vec3{0.0, 0.0, 0.0};
-        x.rng = Rng{1ull, 1ull};
-        x.f.d = 0.0;
-        if (x.live) {
-            x.pos.x = p.pos[3 * w];
-            x.pos.y = p.pos[3 * w + 1];
-            x.pos.z = p.pos[3 * w + 2];
-            ulonglong2 st = reinterpret_cast<const ulonglong2 *>(p.rng)[w];
-            x.rng.s0 = st.x;
-            x.rng.s1 = st.y;
-        }
-#pragma unroll
-        for (int m = 0; m < MR; ++m) x.ph[m] = (x.live && p.t0 > 0) ? p.phases[(long long)m * N + w] : 0.0;
-    };
-    LaneWalker<MR> A, B;
-    load(A, w_a);
-    load(B, w_b);
-
-    // the step is complete: final move, phase update with the post-step position, next time point
-    auto complete = [&](LaneWalker<MR> &x) {
-        x.exc |= end_step<SUB>(x.pos, x.f, p);
-#pragma unroll
-        for (int m = 0; m < MR; ++m) {
-            const double *g = p.grad + ((long long)m * p.n_t + x.t) * 3;
-            double gx = __ldg(g), gy = __ldg(g + 1), gz = __ldg(g + 2);
-            x.ph[m] = fma_(p.gamma_dt, fma_(gz, x.pos.z, fma_(gx, x.pos.x, mul_(gy, x.pos.y))), x.ph[m]);
-        }
-        ++x.t;
-    };
-    auto fresh_step = [&](LaneWalker<MR> &x) {
-        begin_step<SUB>(x.pos, x.rng, p, s_tab, x.f);
-        x.parked = probe<SUB>(x.f, p);
-        if (!x.parked) complete(x);
-    };
-    auto bounce_step = [&](LaneWalker<MR> &x) {
-        bounce<SUB>(x.f, p);
-        x.parked = probe<SUB>(x.f, p);
-        if (!x.parked) complete(x);
-    };
-
-    const unsigned full = 0xffffffffu;
-    for (;;) {
-        const bool run_a = A.live && !A.parked && A.t < p.t1, run_b = B.live && !B.parked && B.t < p.t1;
-        const unsigned m_run = __ballot_sync(full, run_a || run_b);
-        const int n_parked = __popc(__ballot_sync(full, A.parked)) + __popc(__ballot_sync(full, B.parked));
-        if (m_run == 0 && n_parked == 0) break;
-        if (n_parked >= DSB_TWO_WALKERS || m_run == 0) {
-            if (A.parked) bounce_step(A);
-            if (B.parked) bounce_step(B);
-        }
-        // (a walker released by the bounce pass steps again from the next iteration on)
-        if (run_a) fresh_step(A);
-        if (run_b) fresh_step(B);
-    }
-
-    auto store = [&](LaneWalker<MR> &x, long long w) {
-        if (!x.live) return;
-#pragma unroll
-        for (int m = 0; m < MR; ++m) p.phases[(long long)m * N + w] = x.ph[m];
-        if (x.exc) p.iter_exc[w] = 1;
-        else x.exc = p.iter_exc[w] != 0;
-        p.pos[3 * w] = x.pos.x;
-        p.pos[3 * w + 1] = x.pos.y;
-        p.pos[3 * w + 2] = x.pos.z;
-        reinterpret_cast<ulonglong2 *>(p.rng)[w] = make_ulonglong2(x.rng.s0, x.rng.s1);
-    };
-    store(A, w_a);
-    store(B, w_b);
-
-    if (p.finalize) {   // per-block sum of cos(phase) over unflagged walkers, as block_signal lays it out
-        __shared__ double s_part[kBlock / 64][kMaxRegMeas + 1];
-        const bool ok_a = A.live && !A.exc, ok_b = B.live && !B.exc;
-#pragma unroll
-        for (int m = 0; m <= MR; ++m) {
-            double v = 0.0;
-            if (m < MR) {
-                double pa = 0.0, pb = 0.0;
-#pragma unroll
-                for (int k = 0; k < MR; ++k)
-                    if (k == m) pa = A.ph[k], pb = B.ph[k];
-                v = (ok_a ? cos(pa) : 0.0) + (ok_b ? cos(pb) : 0.0);
-            } else {
-                v = (ok_a ? 1.0 : 0.0) + (ok_b ? 1.0 : 0.0);
-            }
-            v = warp_sum(v);
-            if (lane == 0) s_part[warp][m] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x <= MR) {
-            double acc = 0.0;
-#pragma unroll
-            for (int v = 0; v < kBlock / 64; ++v) acc += s_part[v][threadIdx.x];
-            p.partials[(long long)threadIdx.x * p.n_blocks_total + (int)(p.w_begin / kBlock) + blockIdx.x] = acc;
-        }
-    }
-}
-#endif  // DSB_TWO_WALKERS
-
 // ---------------------------------------------------------------- low-rank protocols
 
 // When the (n_meas x 3 n_t) gradient matrix factors as U V with r <= kMaxRank rows in V (every

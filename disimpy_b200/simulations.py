@@ -6,12 +6,18 @@ returned": instead of one Numba launch + stream sync per time step, the walk, th
 accumulation and the sum of cos(phase) run inside libdisimpy_b200.so (hand-written sm_100a
 CUDA behind the C ABI in include/disimpy_b200.h).  There is no CPU fallback.
 
-Multi-GPU: when ``torch.distributed`` is initialised, every rank simulates the contiguous
-walker range ``[rank*N/W, (rank+1)*N/W)`` (or, when the initial positions come from the
-sequential host stream, every W-th part of 131072 walkers) with the walkers' global RNG
-subsequences, and the signal (+ valid-walker count) is summed with one all-reduce; the mesh
-sampler's threads are dealt to the ranks and its accepted points all-gathered.  Results do not
-depend on the number of ranks (up to floating-point summation order of the signal).
+Multi-GPU, two ways (results do not depend on either, up to the floating-point summation
+order of the signal):
+* one process, several GPUs (a plain script; the reference user never launches with torchrun):
+  the walkers are split over the devices of ``local_devices()`` -- every visible GPU unless
+  DISIMPY_B200_DEVICES / DISIMPY_B200_DEVICE say otherwise --, one handle per device driven
+  from this thread (all launches are asynchronous), signals summed on the host;
+* one process per GPU under ``torch.distributed``: every rank simulates the contiguous walker
+  range ``[rank*N/W, (rank+1)*N/W)`` (or, when the initial positions come from the sequential
+  host stream, every W-th part of the stream) with the walkers' global RNG subsequences, and
+  the signal (+ valid-walker count) is summed with ONE all-reduce on the device buffer the
+  library fills; the mesh sampler's threads are dealt to the ranks and its accepted points
+  all-gathered.
 """
 
 import ctypes
@@ -148,12 +154,46 @@ def _write_traj(traj, mode, positions):
         f.write("\n")
 
 
+def _device_count():
+    count = ctypes.c_int32(0)
+    if _lib.lib().dsb_device_count(ctypes.byref(count)) != 0:
+        return 0
+    return count.value
+
+
 def _device():
-    """CUDA device ordinal of this process: DISIMPY_B200_DEVICE, else LOCAL_RANK, else 0."""
-    for name in ("DISIMPY_B200_DEVICE", "LOCAL_RANK"):
-        if os.environ.get(name, "") != "":
-            return int(os.environ[name])
+    """CUDA device ordinal of this process: DISIMPY_B200_DEVICE, else LOCAL_RANK (modulo the number
+    of visible devices: launchers that give every task one visible GPU still count LOCAL_RANK up),
+    else 0."""
+    if os.environ.get("DISIMPY_B200_DEVICE", "") != "":
+        return int(os.environ["DISIMPY_B200_DEVICE"])
+    if os.environ.get("LOCAL_RANK", "") != "":
+        return int(os.environ["LOCAL_RANK"]) % max(_device_count(), 1)
     return 0
+
+
+# a device takes part in a single-process run only if it gets at least this many walkers
+# (DISIMPY_B200_MIN_WALKERS_PER_DEVICE overrides: tests run several handles on small problems)
+_MIN_WALKERS_PER_DEVICE = 131072
+
+
+def local_devices(n_walkers=None):
+    """The device list of a single-process run.  DISIMPY_B200_DEVICES = "all" or a
+    comma-separated list of ordinals picks it; otherwise a process that was given one device
+    (DISIMPY_B200_DEVICE, or LOCAL_RANK from a launcher) uses that one, and a plain script uses
+    every visible GPU.  With ``n_walkers``: no more devices than keep every shard at
+    _MIN_WALKERS_PER_DEVICE walkers or more."""
+    env = os.environ.get("DISIMPY_B200_DEVICES", "").strip()
+    if env and env != "all":
+        devs = [int(x) for x in env.split(",") if x.strip() != ""]
+    elif env == "all" or (os.environ.get("DISIMPY_B200_DEVICE", "") == "" and os.environ.get("LOCAL_RANK", "") == ""):
+        devs = list(range(max(_device_count(), 1)))
+    else:
+        devs = [_device()]
+    if n_walkers is not None:
+        floor = int(os.environ.get("DISIMPY_B200_MIN_WALKERS_PER_DEVICE", _MIN_WALKERS_PER_DEVICE))
+        devs = devs[:max(1, min(len(devs), n_walkers // max(floor, 1)))]
+    return devs
 
 
 def _require_gpu():
@@ -184,21 +224,41 @@ def shard_range(n_walkers, rank, world_size):
     return n_walkers * rank // world_size, n_walkers * (rank + 1) // world_size
 
 
-def owned_ranges(n_walkers, rank, world_size, interleaved=False, part=None):
-    """Which global walkers a rank holds and where: [(global_lo, global_hi, local_lo), ...].
+_PART = 131072        # walkers per part: about one full wave of 128-walker blocks on a B200
+_PART_FIRST = 16384   # the first parts are small, so that every GPU has work after a fraction of a ms
 
-    Contiguous (default): the one range of shard_range.  Interleaved: the parts of ``part``
-    walkers are dealt round-robin to the ranks -- used when the initial positions come from the
-    sequential host stream, so that every rank can start on its first part after 1/world_size of
-    the wait a contiguous shard at the end of the stream would have."""
+
+def part_edges(n_walkers, n_slots=1, part=None):
+    """Boundaries of the parts a pipelined run is dealt in: [0, e1, e2, ..., n_walkers].  A fixed
+    ``part`` gives equal parts; by default the first ``n_slots`` parts hold _PART_FIRST walkers and
+    every further round of ``n_slots`` parts twice as many, up to _PART (all multiples of 128, the
+    walk kernel's block)."""
+    if part is not None:
+        return list(range(0, n_walkers, part)) + [n_walkers]
+    edges, size = [0], _PART_FIRST
+    while edges[-1] < n_walkers:
+        for _ in range(n_slots):
+            if edges[-1] < n_walkers:
+                edges.append(min(edges[-1] + size, n_walkers))
+        size = min(2 * size, _PART)
+    return edges
+
+
+def owned_ranges(n_walkers, rank, world_size, interleaved=False, part=None):
+    """Which global walkers a rank (or a device of a single-process run) holds and where:
+    [(global_lo, global_hi, local_lo), ...].
+
+    Contiguous (default): the one range of shard_range.  Interleaved: the parts of part_edges are
+    dealt round-robin -- used when the initial positions come from the sequential host stream, so
+    that everybody can start on a first part at once instead of after everything that precedes a
+    contiguous shard in the stream."""
     if not interleaved:
         lo, hi = shard_range(n_walkers, rank, world_size)
         return [(lo, hi, 0)]
-    part = _PART if part is None else part
+    edges = part_edges(n_walkers, world_size, part)
     out, local = [], 0
-    for k, a in enumerate(range(0, n_walkers, part)):
+    for k, (a, b) in enumerate(zip(edges[:-1], edges[1:])):
         if k % world_size == rank:
-            b = min(a + part, n_walkers)
             out.append((a, b, local))
             local += b - a
     return out
@@ -284,6 +344,10 @@ class Walk:
         _lib.check(self._L.dsb_get_signal(self._h, _lib.ptr(sig), ctypes.byref(n_valid)),
                    "dsb_get_signal")
         return sig, n_valid.value
+
+    def copy_signal_to(self, dev_ptr):
+        """The n_meas + 1 result doubles (sum cos, valid count) into a device buffer of the caller."""
+        _lib.check(self._L.dsb_copy_signal_dev(self._h, ctypes.c_void_p(dev_ptr)), "dsb_copy_signal_dev")
 
     def positions(self):
         out = np.zeros((self.n_walkers, 3))
@@ -480,98 +544,234 @@ def simulation(
             if not quiet:
                 print("Finished calculating initial positions")
 
-    rank, world, dist = _dist()
-    # the parts of a pipelined run are dealt round-robin to the ranks (if there are enough of them)
-    interleaved = pipelined and world > 1 and (n_walkers + _PART - 1) // _PART >= world
-    owned = owned_ranges(n_walkers, rank, world, interleaved)
-    lo, hi = owned[0][0], owned[0][1]          # (the contiguous shard when not interleaved)
-    n_local = sum(b - a for a, b, _ in owned)
-    if traj and rank == 0 and not device_fill:
-        _write_traj(traj, "w", positions)
-
-    params, keep = make_params(substrate, n_local, lo, gradient, dt, step_l, seed, max_iter,
-                               epsilon)
-    walk = Walk(params, gradient)
+    trace = _Trace()
+    shards = _Shards(substrate, n_walkers, gradient, dt, step_l, seed, max_iter, epsilon, pipelined)
+    dist, rank = shards.dist, shards.rank
+    trace("handles")
     try:
-        if interleaved:
-            for a, b, la in owned:
-                walk.set_rng_part(la, la + b - a, a)
+        if traj and rank == 0 and not device_fill:
+            _write_traj(traj, "w", positions)
         if pipelined:
-            _walk_pipelined(walk, substrate, owned, seed)
+            _walk_pipelined(shards, substrate, seed, trace)
         elif device_fill:
-            if world > 1 and dist.get_backend() == "nccl" and n_walkers >= _SHARDED_FILL_MIN:
-                _fill_mesh_sharded(walk, substrate, n_walkers, lo, n_local, seed, rank, world, dist)
-            else:
-                walk.fill_mesh(substrate.voxel_size, substrate.init_pos == "intra", seed, n_walkers, lo, cuda_bs)
+            shards.fill_mesh(substrate, seed, cuda_bs)
             if traj:
-                start = _gather_rows(walk.positions(), n_walkers, owned, dist)
+                start = shards.rows(lambda w: w.positions())
                 if rank == 0:
                     _write_traj(traj, "w", start)
         else:
-            walk.set_positions(positions[lo:hi])
+            shards.set_positions(positions)
+        trace("positions")
         if pipelined:
             pass
         elif traj:
             for t in range(n_t):
-                walk.run(t, t + 1)
-                step_pos = _gather_rows(walk.positions(), n_walkers, owned, dist)
+                shards.run(t, t + 1)
+                step_pos = shards.rows(lambda w: w.positions())
                 if rank == 0:
                     _write_traj(traj, "a", step_pos)
                 if not quiet:
                     sys.stdout.write(f"\r{np.round((t / n_t) * 100, 1)}%")
                     sys.stdout.flush()
         elif quiet:
-            walk.run(0, n_t)
-        else:  # a handful of launches so that progress can be shown (cut on multiples of 8 steps:
-            # the many-measurement kernels work in 8-step chunks)
+            shards.run(0, n_t)
+        else:  # a handful of launches so that progress can be shown, cut on multiples of 16 steps (the
+            # many-measurement kernels work in chunks of 16 steps, 8 for a mesh)
             edges = np.linspace(0, n_t, min(n_t, 20) + 1).astype(int)
-            edges[1:-1] = (edges[1:-1] + 4) // 8 * 8
+            edges[1:-1] = (edges[1:-1] + 8) // 16 * 16
             edges = np.unique(np.clip(edges, 0, n_t))
             for t0, t1 in zip(edges[:-1], edges[1:]):
                 sys.stdout.write(f"\r{np.round((t0 / n_t) * 100, 1)}%")
                 sys.stdout.flush()
-                walk.run(int(t0), int(t1))
-                walk.sync()
+                shards.run(int(t0), int(t1))
+                shards.sync()
+        trace("submitted")
 
-        # The signal kernel also counts the walkers whose iter_exc flag is clear, so the
-        # per-walker flags only travel to the host when something was flagged (or when the
-        # caller asked for per-walker output).
-        if all_signals:
-            iter_exc = walk.iter_exc()
-            n_flagged = int(iter_exc.sum())
-        else:
-            signals, n_valid = walk.signal()
-            n_flagged = n_local - n_valid
-            iter_exc = None
-        if dist is not None:
-            n_flagged = int(round(_allreduce_sum(np.array([float(n_flagged)]), dist)[0]))
+        # The signal kernel also counts the walkers whose iter_exc flag is clear, so the per-walker
+        # flags only travel to the host when something was flagged (or when the caller asked for
+        # per-walker output).  One collective for signal and count together.
+        signals, n_valid = shards.signal(trace)
+        n_flagged = n_walkers - n_valid
+        iter_exc_all = None
+        if n_flagged > 0 or all_signals:
+            iter_exc_all = shards.rows(lambda w: w.iter_exc())
         if n_flagged > 0:
-            if iter_exc is None:
-                iter_exc = walk.iter_exc()
-            iter_exc_all = _gather_rows(iter_exc, n_walkers, owned, dist)
             warnings.warn(
                 "Maximum number of iterations was exceeded in the intersection "
                 + "check algorithm for walkers %s" % np.where(iter_exc_all)[0])
 
         if all_signals:
-            phases = walk.phases()
-            phases[:, np.where(iter_exc)[0]] = np.nan
+            phases = shards.rows(lambda w: w.phases().T).T
+            phases[:, np.where(iter_exc_all)[0]] = np.nan
             signals = np.real(np.exp(1j * phases))
-            signals = _gather_rows(signals.T, n_walkers, owned, dist).T
-        elif dist is not None:
-            signals = _allreduce_sum(signals, dist)
         if not quiet:
             sys.stdout.write("\rSimulation finished\n")
             sys.stdout.flush()
         if final_pos:
-            final = _gather_rows(walk.positions(), n_walkers, owned, dist)
+            final = shards.rows(lambda w: w.positions())
+            trace("done")
             return signals, final
+        trace("done")
         return signals
     finally:
-        walk.close()
+        shards.close()
+        trace.report()
 
 
-_PART = 131072  # walkers per part: about one full wave of 128-walker blocks on a B200
+class _Trace:
+    """DISIMPY_B200_TRACE=1: host time stamps of the phases of a simulation() call, printed to stderr
+    as one JSON line per call (where does the end-to-end time go next to the kernel time)."""
+
+    def __init__(self):
+        self.on = os.environ.get("DISIMPY_B200_TRACE", "") not in ("", "0")
+        if self.on:
+            import time
+            self._clock = time.perf_counter
+            self.t0 = self._clock()
+            self.marks = []
+
+    def __call__(self, label):
+        if self.on:
+            self.marks.append((label, round(1e3 * (self._clock() - self.t0), 3)))
+
+    def report(self):
+        if self.on:
+            import json
+            sys.stderr.write("disimpy_b200 trace (ms since entry): " + json.dumps(self.marks) + "\n")
+            sys.stderr.flush()
+
+
+class _Shards:
+    """The handles this process drives: one per device of local_devices() in a single-process run, or
+    the one of a rank under torch.distributed.  Slot k of n_slots (= ranks x local devices) holds the
+    global walkers owned_ranges(n_walkers, k, n_slots, interleaved)."""
+
+    def __init__(self, substrate, n_walkers, gradient, dt, step_l, seed, max_iter, epsilon, pipelined):
+        self.rank, self.world, self.dist = _dist()
+        devices = [_device()] if self.dist is not None else local_devices(n_walkers)
+        self.n_walkers, self.n_meas = n_walkers, gradient.shape[0]
+        self.n_slots = self.world * len(devices)
+        # the parts of a pipelined run are dealt round-robin (if there are enough of them)
+        self.interleaved = (pipelined and self.n_slots > 1
+                            and len(part_edges(n_walkers, self.n_slots)) - 1 >= self.n_slots)
+        self.walks, self.owned = [], []
+        try:
+            for j, dev in enumerate(devices):
+                owned = owned_ranges(n_walkers, self.rank * len(devices) + j, self.n_slots, self.interleaved)
+                n_local = sum(b - a for a, b, _ in owned)
+                walk = None
+                if n_local > 0:   # (fewer walkers than slots: the empty ones contribute nothing)
+                    params, keep = make_params(substrate, n_local, owned[0][0], gradient, dt, step_l, seed, max_iter,
+                                               epsilon, device=dev)
+                    walk = Walk(params, gradient)
+                    if self.interleaved:
+                        for a, b, la in owned:
+                            walk.set_rng_part(la, la + b - a, a)
+                self.walks.append(walk)
+                self.owned.append(owned)
+        except Exception:
+            self.close()
+            raise
+
+    def live(self):
+        return [(w, o) for w, o in zip(self.walks, self.owned) if w is not None]
+
+    def set_positions(self, positions):
+        for w, owned in self.live():
+            (lo, hi, _), = owned
+            w.set_positions(positions[lo:hi])
+
+    def run(self, t0, t1):
+        for w, _ in self.live():
+            w.run(t0, t1)
+
+    def sync(self):
+        for w, _ in self.live():
+            w.sync()
+
+    def fill_mesh(self, substrate, seed, cuda_bs):
+        """Initial positions of a periodic mesh, drawn on the GPU(s) and left there."""
+        intra = substrate.init_pos == "intra"
+        live = self.live()
+        if self.dist is not None:
+            if self.dist.get_backend() == "nccl" and self.n_walkers >= _SHARDED_FILL_MIN and all(w is not None for w in self.walks):
+                (lo, hi, _), = self.owned[0]
+                _fill_mesh_sharded(self.walks[0], substrate, self.n_walkers, lo, hi - lo, seed, self.rank, self.world,
+                                   self.dist)
+            else:
+                for w, ((lo, _, _),) in live:
+                    w.fill_mesh(substrate.voxel_size, intra, seed, self.n_walkers, lo, cuda_bs)
+        elif len(live) == 1:
+            live[0][0].fill_mesh(substrate.voxel_size, intra, seed, self.n_walkers, live[0][1][0][0], cuda_bs)
+        else:   # the device list of one process: the sampler's threads are dealt to the devices (in the library)
+            handles = (ctypes.c_void_p * len(live))(*[w._h for w, _ in live])
+            voxel = _lib.f64(substrate.voxel_size)
+            _lib.check(_lib.lib().dsb_fill_mesh_multi(handles, len(live), _lib.ptr(voxel), 1 if intra else 0, seed,
+                                                      self.n_walkers), "dsb_fill_mesh_multi")
+
+    def signal(self, trace=None):
+        """(sum over ALL walkers of cos(phase) per measurement, number of unflagged walkers): local
+        handles summed in slot order, then one all-reduce over the ranks."""
+        total = np.zeros(self.n_meas + 1)
+        live = self.live()
+        if self.dist is not None and self.dist.get_backend() == "nccl":
+            # the library copies its (n_meas + 1) result doubles into the tensor NCCL reduces in place
+            import torch
+            t = torch.zeros(self.n_meas + 1, dtype=torch.float64, device="cuda:%d" % _device())
+            if live:
+                torch.cuda.current_stream(t.device).synchronize()   # (the zero fill precedes the library's copy)
+                live[0][0].copy_signal_to(t.data_ptr())
+            if trace:
+                trace("walk finished")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            total = t.cpu().numpy()
+        else:
+            for w, _ in live:
+                sig, n_valid = w.signal()
+                total[:-1] += sig
+                total[-1] += n_valid
+            if trace:
+                trace("walk finished")
+            if self.dist is not None:
+                total = _allreduce_sum(total, self.dist)
+        if trace:
+            trace("signal reduced")
+        return total[:-1].copy(), int(round(total[-1]))
+
+    def rows(self, fetch):
+        """Per-walker rows (fetch(walk) -> array with one row per local walker) of all walkers, in
+        global order, on every rank (only used for final_pos / all_signals / traj / the iter_exc
+        warning: per-shard host gathers, no device collective)."""
+        pieces = [(owned, fetch(w)) for w, owned in self.live()]
+        return _assemble_rows(pieces, self.n_walkers, self.dist)
+
+    def close(self):
+        for w in self.walks:
+            if w is not None:
+                w.close()
+        self.walks = []
+
+
+def _stream_sampler(substrate, seed):
+    """(sampler over the sequential host stream of an analytic substrate, function that turns a
+    stretch of the stream into lab-frame positions): simulations.py:346-418."""
+    if substrate.type == "sphere":
+        sampler, to_lab = _HostSampler(1, seed, substrate.radius, 3), None
+    elif substrate.type == "cylinder":
+        R = utils.vec2vec_rotmat(substrate.orientation, np.array([1.0, 0, 0]))
+        sampler, to_lab = _HostSampler(0, seed, substrate.radius, 2), np.linalg.inv(R)
+    else:
+        sampler, to_lab = _HostSampler(2, seed, substrate.semiaxes, 3), substrate.R
+
+    def finish(pts):
+        if substrate.type == "cylinder":
+            body = np.zeros((len(pts), 3))
+            body[:, 1:3] = pts
+            pts = body
+        if to_lab is not None:
+            pts = np.matmul(to_lab, pts.T).T
+        return pts
+    return sampler, finish
 
 
 def _position_parts(substrate, lo, hi, seed, part=_PART, wanted=None):
@@ -580,13 +780,7 @@ def _position_parts(substrate, lo, hi, seed, part=_PART, wanted=None):
     _fill_sphere / _initial_positions_cylinder / _initial_positions_ellipsoid return in one go
     (simulations.py:346-418).  Parts for which ``wanted(a, b)`` is false are drawn (the stream is
     sequential) but not yielded."""
-    if substrate.type == "sphere":
-        sampler, to_lab = _HostSampler(1, seed, substrate.radius, 3), None
-    elif substrate.type == "cylinder":
-        R = utils.vec2vec_rotmat(substrate.orientation, np.array([1.0, 0, 0]))
-        sampler, to_lab = _HostSampler(0, seed, substrate.radius, 2), np.linalg.inv(R)
-    else:
-        sampler, to_lab = _HostSampler(2, seed, substrate.semiaxes, 3), substrate.R
+    sampler, finish = _stream_sampler(substrate, seed)
     try:
         sampler.skip(lo)
         n = hi - lo
@@ -595,34 +789,40 @@ def _position_parts(substrate, lo, hi, seed, part=_PART, wanted=None):
             pts = sampler.next(b - a)
             if wanted is not None and not wanted(a, b):
                 continue
-            if substrate.type == "cylinder":
-                body = np.zeros((b - a, 3))
-                body[:, 1:3] = pts
-                pts = body
-            if to_lab is not None:
-                pts = np.matmul(to_lab, pts.T).T
-            yield a, b, pts
+            yield a, b, finish(pts)
     finally:
         sampler.close()
 
 
-def _walk_pipelined(walk, substrate, owned, seed):
+def _walk_pipelined(shards, substrate, seed, trace=None):
     """Walks every part over all time steps as soon as its positions are there: the host draws
-    the next part while the GPU works.  Same positions, same walk, same signal as drawing
-    everything first.  ``owned``: the rank's walkers (owned_ranges)."""
-    walk.rewind()
-    if len(owned) == 1:   # one contiguous shard: skip to it, then part by part
-        lo, hi, _ = owned[0]
-        for a, b, pts in _position_parts(substrate, lo, hi, seed):
-            walk.set_positions_part(a, b, pts)
-            walk.run_part(a, b)
-    else:                 # parts dealt round-robin: draw the whole stream, keep this rank's parts
-        local_of = {a: la for a, _, la in owned}
-        for a, b, pts in _position_parts(substrate, 0, owned[-1][1], seed, wanted=lambda a, b: a in local_of):
-            la = local_of[a]
-            walk.set_positions_part(la, la + b - a, pts)
-            walk.run_part(la, la + b - a)
-    walk.finish()
+    the next part while the GPUs work.  Same positions, same walk, same signal as drawing
+    everything first.  One pass over the sequential stream serves every local handle; stretches
+    that belong to other ranks are drawn and dropped."""
+    jobs = []   # (global lo, global hi, handle, local lo), in stream order
+    for w, owned in shards.live():
+        w.rewind()
+        if shards.interleaved:
+            jobs += [(a, b, w, la) for a, b, la in owned]
+        else:      # one contiguous shard per handle, walked in parts of growing size
+            (lo, hi, _), = owned
+            edges = part_edges(hi - lo)
+            jobs += [(lo + a, lo + b, w, a) for a, b in zip(edges[:-1], edges[1:])]
+    jobs.sort(key=lambda j: j[0])
+    sampler, finish = _stream_sampler(substrate, seed)
+    try:
+        at = 0
+        for k, (a, b, w, la) in enumerate(jobs):
+            sampler.skip(a - at)
+            w.set_positions_part(la, la + b - a, finish(sampler.next(b - a)))
+            w.run_part(la, la + b - a)
+            at = b
+            if trace and k == 0:
+                trace("first part submitted")
+    finally:
+        sampler.close()
+    for w, _ in shards.live():
+        w.finish()
 
 
 # from this many walkers on, the ranks of a multi-GPU run share the work of the mesh sampler
@@ -689,16 +889,23 @@ def _allreduce_sum(values, dist):
     return t.cpu().numpy()
 
 
+def _assemble_rows(pieces, n_total, dist):
+    """pieces: [(owned ranges, rows of those walkers), ...] held by this process -> the rows of all
+    n_total walkers in global order, on every rank."""
+    if dist is not None:
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, pieces)
+        pieces = [p for rank_pieces in out for p in rank_pieces]
+    shape, dtype = next(((rows.shape[1:], rows.dtype) for _, rows in pieces), ((), np.float64))
+    full = np.zeros((n_total,) + shape, dtype=dtype)
+    for ranges, rows in pieces:
+        for a, b, la in ranges:
+            full[a:b] = rows[la:la + b - a]
+    return full
+
+
 def _gather_rows(local, n_total, owned, dist):
     """Assemble per-walker rows from all ranks (only used for final_pos / all_signals / traj
     / the iter_exc warning -- per-shard host gathers, no device collective).  ``owned``: this
     rank's walkers as owned_ranges returns them."""
-    if dist is None:
-        return local
-    out = [None] * dist.get_world_size()
-    dist.all_gather_object(out, (owned, local))
-    full = np.zeros((n_total,) + local.shape[1:], dtype=local.dtype)
-    for ranges, rows in out:
-        for a, b, la in ranges:
-            full[a:b] = rows[la:la + b - a]
-    return full
+    return _assemble_rows([(owned, local)], n_total, dist)

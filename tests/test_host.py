@@ -473,3 +473,42 @@ def test_gradient_helpers_bit_equal_to_reference(tmp_path):
     path.write_text("VERSION: 1\n")
     with pytest.raises(Exception):
         gradients.load_camino_scheme_file(str(path))
+
+
+def test_part_edges_and_device_list(monkeypatch):
+    """Host logic of the pipelined / device-list run: parts grow from 16384 to 131072 walkers, are
+    multiples of the kernel's 128-walker block, and tile the walkers; the device list follows the
+    environment."""
+    from disimpy_b200 import simulations as S
+    for n, slots in ((1, 1), (16384, 1), (1_000_000, 1), (8_000_000, 8), (300_000, 3)):
+        e = S.part_edges(n, slots)
+        assert e[0] == 0 and e[-1] == n and all(a < b for a, b in zip(e[:-1], e[1:]))
+        assert all(x % 128 == 0 for x in e[:-1])
+        sizes = np.diff(e)
+        assert sizes.max() <= 131072 and (len(sizes) <= slots or sizes[slots - 1] <= 16384)
+        seen = np.zeros(n, dtype=int)
+        for k in range(slots):
+            local = 0
+            for a, b, la in S.owned_ranges(n, k, slots, interleaved=True):
+                assert la == local and la % 128 == 0
+                seen[a:b] += 1
+                local += b - a
+        assert np.all(seen == 1)
+    monkeypatch.setattr(S, "_device_count", lambda: 4)
+    for k in ("DISIMPY_B200_DEVICES", "DISIMPY_B200_DEVICE", "LOCAL_RANK", "DISIMPY_B200_MIN_WALKERS_PER_DEVICE"):
+        monkeypatch.delenv(k, raising=False)
+    assert S.local_devices() == [0, 1, 2, 3]                       # a plain script: every visible GPU
+    assert S.local_devices(300_000) == [0, 1]                      # ... that gets at least 131072 walkers
+    assert S.local_devices(10) == [0]
+    monkeypatch.setenv("LOCAL_RANK", "6")
+    assert S.local_devices() == [2] and S._device() == 2           # a launcher's rank, modulo the visible devices
+    monkeypatch.setenv("DISIMPY_B200_DEVICE", "3")
+    assert S.local_devices() == [3]
+    monkeypatch.setenv("DISIMPY_B200_DEVICES", "1,3")
+    assert S.local_devices() == [1, 3]
+    monkeypatch.setenv("DISIMPY_B200_DEVICES", "all")
+    assert S.local_devices() == [0, 1, 2, 3]
+    # rows of several local handles and interleaved ranges go back into global order
+    rows = S._assemble_rows([([(0, 2, 0), (4, 5, 2)], np.array([[0.0], [1.0], [4.0]])),
+                             ([(2, 4, 0)], np.array([[2.0], [3.0]]))], 5, None)
+    assert np.array_equal(rows[:, 0], np.arange(5.0))

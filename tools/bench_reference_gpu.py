@@ -4,7 +4,8 @@ B200"; a reported baseline, not an optimisation target).
 
 Test/measurement infrastructure only: imports the reference from oracle/_ref (git-ignored pip
 install of /root/reference).  Run:  gpurun -- python tools/bench_reference_gpu.py
-Writes gpurun_out/reference_numba_gpu.json.
+Writes gpurun_out/reference_numba_gpu.json.  With --json (what bench.py's `baselines` leg runs) the
+progress lines go to stderr and ONE JSON line to stdout.
 
 Two figures per workload:
   e2e          wall time of disimpy.simulations.simulation(..., quiet=True) after a JIT warm-up
@@ -33,6 +34,11 @@ from disimpy_b200 import meshgen  # noqa: E402
 
 D = 2e-9
 out = {}
+JSON_ONLY = "--json" in sys.argv
+
+
+def say(*a):
+    print(*a, file=sys.stderr if JSON_ONLY else sys.stdout, flush=True)
 
 
 def pgse(n_t, n_meas=1):
@@ -53,7 +59,7 @@ def e2e(name, sub, n, n_t, n_meas=1):
     el = time.time() - t0
     out[name + "_e2e"] = dict(n_walkers=n, n_t=n_t, n_meas=n_meas, seconds=el,
                               walker_steps_per_s=n * n_t / el)
-    print(name, "e2e", out[name + "_e2e"], flush=True)
+    say(name, "e2e", out[name + "_e2e"])
 
 
 def kernel_only(name, sub, n, n_t, positions, n_meas=1):
@@ -96,12 +102,15 @@ def kernel_only(name, sub, n, n_t, positions, n_meas=1):
     ms = cuda.event_elapsed_time(e0, e1)
     out[name + "_kernel_only"] = dict(n_walkers=n, n_t=n_t - 1, n_meas=n_meas, ms=ms,
                                       walker_steps_per_s=n * (n_t - 1) / (ms * 1e-3))
-    print(name, "kernel-only", out[name + "_kernel_only"], flush=True)
+    say(name, "kernel-only", out[name + "_kernel_only"])
 
 
 def main():
     import numba
     out["versions"] = dict(numba=numba.__version__, device=str(cuda.get_current_device().name))
+    out["what"] = ("the unmodified reference (disimpy 0.3.0, its Numba-CUDA kernels) on this GPU: *_e2e = its "
+                   "simulation(..., quiet=True) call; *_kernel_only = its step kernels launched for all time steps "
+                   "between CUDA events, without its per-step stream.synchronize() / the mesh loop's time.sleep(1e-2)")
     sph = substrates.sphere(10e-6)
     e2e("sphere_1e6x1e4", sph, 1_000_000, 10_000)
     kernel_only("sphere_1e6x1e4", sph, 1_000_000, 10_000, S._fill_sphere(1_000_000, 10e-6))
@@ -110,11 +119,15 @@ def main():
     mesh = substrates.mesh(v, f, True, padding=pad, init_pos="uniform", n_sv=np.array([50, 50, 50]),
                            quiet=True)
     out["mesh_subdivision_seconds"] = time.time() - t0
-    print("reference mesh subdivision: %.1f s for %d triangles" % (time.time() - t0, len(f)), flush=True)
+    say("reference mesh subdivision: %.1f s for %d triangles" % (time.time() - t0, len(f)))
     np.random.seed(123)
     pos = np.random.random((1_000_000, 3)) * mesh.voxel_size
     kernel_only("mesh_98k_1e6x1e3", mesh, 1_000_000, 1000, pos)
     e2e("mesh_98k_1e5x200", mesh, 100_000, 200)
+    if JSON_ONLY:
+        print(json.dumps(out), flush=True)
+        return
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "reference_numba_gpu.json"), "w") as fh:
         json.dump(out, fh, indent=1)
     print(json.dumps(out, indent=1))
