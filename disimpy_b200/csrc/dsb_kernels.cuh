@@ -959,13 +959,19 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
         //    is used);
         //  * Phi: 8 x 8 accumulator tiles straight from / to the (n_meas, n_walkers) array with
         //    evict-first accesses, requested one group of 8 measurements ahead; one round trip
-        //    through HBM per chunk.
+        //    through HBM per chunk.  (Measured in round 2, profiles/r02_c_kbench_variants.txt: with
+        //    L2-resident hints -- ld/st.cg, 3 or 4 blocks per SM so that the resident tiles, 82-109 MB
+        //    at 180 measurements, fit the 126 MB L2 -- the sphere runs at 1.02e10 walker-steps/s
+        //    against 1.34e10 with evict-first: the tiles of retired blocks crowd out the live ones.)
         // Summation order and roundings differ from the reference's fma chain at the 1e-16 level
         // (phases for n_meas > 4 agree to ~1e-13, not bit for bit; positions are not affected).
         // The ragged end of a run (fewer than C steps) uses the reference's formula.
-        if (active && p.t0 == 0)
-            for (int m = 0; m < p.n_meas; ++m) p.phases[(long long)m * N + w] = 0.0;
         constexpr int C = ChunkSteps<SUB>::value, kRows = 3 * C, kRowLen = grad_row_len(C);
+        // a run that starts with a whole chunk starts its accumulators at zero instead of reading
+        // zeros it would have had to write first
+        const bool first_chunk_whole = p.t0 == 0 && p.t1 >= C;
+        if (active && p.t0 == 0 && !first_chunk_whole)
+            for (int m = 0; m < p.n_meas; ++m) p.phases[(long long)m * N + w] = 0.0;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         // the warp's position tile: rows k = 3 * step + axis, 32 columns = lanes, column c of row k
         // kept at c ^ ((k & 3) << 3).  The mesh walk keeps its positions in local memory while it
@@ -1025,7 +1031,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                 const long long w_warp = w - lane;  // first walker of the warp
                 auto load_c = [&](int m0, double (&c)[4][2]) {
                     const int m = m0 + g8;
-                    const bool row_ok = m < p.n_meas;
+                    const bool row_ok = m < p.n_meas && !(first_chunk_whole && t == 0);
                     const double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {

@@ -3,7 +3,8 @@
 ): signals, final positions and per-walker signals of the sharded run must equal the single-GPU
 run of the same call -- positions bit for bit, signals to summation-order rounding -- for the
 pipelined path with round-robin parts, for a small run (contiguous shards), a many-measurement
-protocol and a mesh."""
+protocol, a mesh, and a run with fewer walkers than ranks.  Then rank 0 alone repeats the calls as a
+single process driving all the GPUs (the device list of SURVEY.md 8b)."""
 import os
 import sys
 import time
@@ -32,6 +33,7 @@ cases = [("sphere 600k (round-robin parts)", 600_000, g1, dt1, substrates.sphere
 simulations._SHARDED_FILL_MIN = 0     # the mesh sampler's threads are dealt to the ranks even for this small run
 mesh_intra = substrates.mesh(v, f, True, padding=pad, init_pos="intra", n_sv=np.array([8, 8, 6]), quiet=True)
 cases.append(("periodic mesh 30001, init_pos intra", 30_001, g1, dt1, mesh_intra))
+cases.append(("sphere, 1 walker (fewer walkers than ranks: empty shards)", 1, g1, dt1, substrates.sphere(5e-6)))
 real_dist = simulations._dist
 for name, n, g, dt, sub in cases:
     t0 = time.time()
@@ -49,3 +51,21 @@ for name, n, g, dt, sub in cases:
         print("ok  %-40s %d ranks, %.0f ms" % (name, world, 1e3 * t_multi), flush=True)
 dist.barrier()
 dist.destroy_process_group()
+
+# The device list of ONE process (a plain script on a multi-GPU box, no torchrun): rank 0 alone drives
+# all the GPUs of the job and must get what one GPU gives.
+if rank == 0:
+    os.environ.pop("DISIMPY_B200_DEVICE", None)
+    os.environ["DISIMPY_B200_MIN_WALKERS_PER_DEVICE"] = "1000"
+    for name, n, g, dt, sub in cases[:-1]:
+        out = {}
+        for devs in (",".join(str(d) for d in range(world)), "0"):
+            os.environ["DISIMPY_B200_DEVICES"] = devs
+            t0 = time.time()
+            sig, pos = simulations.simulation(n, 2e-9, g, dt, sub, seed=5, final_pos=True, quiet=True)
+            out[devs] = (sig, pos, time.time() - t0)
+        (sig, pos, t_multi), (sig1, pos1, t_one) = out.values()
+        assert np.array_equal(pos, pos1), name
+        assert np.allclose(sig, sig1, rtol=1e-12, atol=0), name
+        print("ok  %-40s one process, devices %s: %.0f ms (device 0 alone: %.0f ms)"
+              % (name, list(out)[0], 1e3 * t_multi, 1e3 * t_one), flush=True)
