@@ -370,8 +370,18 @@ struct MeshBuffers {
     int *col_start = nullptr, *col_cnt = nullptr;
     uint4 *col_entry = nullptr;
     dsb::FillColumns columns{};
+    // the refined search grid (null when the walk searches the reference grid itself)
+    uint4 *f_entry = nullptr;
+    int2 *f_cell_rng = nullptr;
+    double *f_xs = nullptr, *f_ys = nullptr, *f_zs = nullptr;
+    int refine[3] = {1, 1, 1};
     void release()
     {
+        cache_free(f_entry);
+        cache_free(f_cell_rng);
+        cache_free(f_xs);
+        cache_free(f_ys);
+        cache_free(f_zs);
         cache_free(col_start);
         cache_free(col_cnt);
         cache_free(col_entry);
@@ -390,7 +400,157 @@ struct MeshBuffers {
 // Re-lays the reference's mesh arrays out for the kernels: int64 indices become int32, and the
 // three vertex gathers per test (simulations.py:100-118) become one 16-byte aligned 80-byte
 // record per triangle holding A, B-A, C-A (72 bytes) and a pad, read with five 128-bit loads.
-int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
+// How finely the search grid cuts the reference's cells, per axis.  The collision search reads the
+// lists of the cells the remaining step segment overlaps; with cells much larger than the step most
+// of a list is far from the segment.  Cutting a cell into sub-cells not smaller than 1.05 steps keeps
+// a segment within two sub-cells per axis (the kernel's short-step variant) and shortens the lists
+// it reads (measured on the 1e6-triangle mesh of BASELINE config 5, 1.92 um cells, 0.69 um steps).
+// DISIMPY_B200_REFINE = "kx,ky,kz" overrides (tests force odd factors), "0" or "1" turns it off.
+void choose_refinement(const dsb_mesh &m, double step_l, int64_t n_entries, int k[3])
+{
+    k[0] = k[1] = k[2] = 1;
+    const char *env = getenv("DISIMPY_B200_REFINE");
+    if (env && *env) {
+        int a = 1, b = 1, c = 1;
+        const int got = sscanf(env, "%d,%d,%d", &a, &b, &c);
+        if (got == 1) b = c = a;
+        if (got >= 1) {
+            k[0] = std::min(std::max(a, 1), 8);
+            k[1] = std::min(std::max(b, 1), 8);
+            k[2] = std::min(std::max(c, 1), 8);
+        }
+    } else {
+        if (!(step_l > 0)) return;
+        const double *grid[3] = {m.xs, m.ys, m.zs};
+        for (int a = 0; a < 3; ++a) {
+            const double h = (grid[a][m.n_sv[a]] - grid[a][0]) / (double)m.n_sv[a];
+            const double f = std::floor(h / (1.05 * step_l));
+            k[a] = f >= 4.0 ? 4 : (f >= 1.0 ? (int)f : 1);
+        }
+    }
+    // bounded tables: at most 2^24 sub-cells, and (a triangle is listed once per sub-cell its box
+    // reaches into) not more than about 2^26 entries
+    const int64_t n_cells = m.n_sv[0] * m.n_sv[1] * m.n_sv[2];
+    for (;;) {
+        const int64_t kk = (int64_t)k[0] * k[1] * k[2];
+        if (kk == 1 || (n_cells * kk <= (int64_t(1) << 24) && n_entries * kk <= (int64_t(1) << 26))) break;
+        int big = 0;
+        for (int a = 1; a < 3; ++a)
+            if (k[a] > k[big]) big = a;
+        --k[big];
+    }
+}
+
+// The refined search grid (dsb::SearchGrid): boundaries, per-sub-cell ranges and entry records.  A
+// sub-cell lists, in the parent's order, the triangles of its parent cell whose bounding box, padded
+// by 1e-9 of the voxel, reaches into it (closed intervals): a superset of the triangles that touch
+// the sub-cell, a subset of the parent's list.
+int build_search_grid(const dsb_mesh &m, const HostBuf<int2> &cells, const HostBuf<int> &tri_idx, const HostBuf<uint4> &box,
+                      const int k[3], MeshBuffers &mb)
+{
+    Range nvtx("dsb: refined search grid");
+    const int64_t n[3] = {m.n_sv[0], m.n_sv[1], m.n_sv[2]};
+    const int64_t nf[3] = {n[0] * k[0], n[1] * k[1], n[2] * k[2]};
+    const int64_t n_fine = nf[0] * nf[1] * nf[2];
+    const double *grid[3] = {m.xs, m.ys, m.zs};
+    std::vector<double> fb[3];
+    for (int a = 0; a < 3; ++a) {
+        fb[a].resize((size_t)nf[a] + 1);
+        for (int64_t i = 0; i < n[a]; ++i)
+            for (int j = 0; j < k[a]; ++j)
+                fb[a][(size_t)(i * k[a] + j)] = j == 0 ? grid[a][i] : grid[a][i] + (grid[a][i + 1] - grid[a][i]) * ((double)j / k[a]);
+        fb[a][(size_t)nf[a]] = grid[a][n[a]];
+        for (int64_t i = 0; i < nf[a]; ++i)
+            if (!(fb[a][(size_t)i] < fb[a][(size_t)i + 1])) return fail(DSB_EINVAL, "mesh: subvoxel boundaries are not increasing");
+    }
+    // padded bounding boxes of the triangles
+    HostBuf<double> tb((size_t)m.n_faces * 6);
+    if (!tb.ok()) return fail(DSB_ENOMEM, "mesh: no page-locked host memory for the search grid");
+    double pad[3];
+    for (int a = 0; a < 3; ++a) pad[a] = 1e-9 * std::fabs(grid[a][n[a]] - grid[a][0]);
+    parallel_ranges(m.n_faces, [&](int64_t f0, int64_t f1) {
+        for (int64_t f = f0; f < f1; ++f) {
+            const int64_t *idx = m.faces + 3 * f;
+            for (int a = 0; a < 3; ++a) {
+                const double p = m.vertices[3 * idx[0] + a], q = m.vertices[3 * idx[1] + a], r = m.vertices[3 * idx[2] + a];
+                double lo = std::min(p, std::min(q, r)) - pad[a], hi = std::max(p, std::max(q, r)) + pad[a];
+                if (!(lo == lo) || !(hi == hi)) lo = -INFINITY, hi = INFINITY;   // NaN vertex: listed everywhere
+                tb[(size_t)f * 6 + a] = lo;
+                tb[(size_t)f * 6 + 3 + a] = hi;
+            }
+        }
+    });
+    HostBuf<int2> fcells((size_t)n_fine);
+    if (!fcells.ok()) return fail(DSB_ENOMEM, "mesh: no page-locked host memory for the search grid");
+    const int64_t n_coarse = n[0] * n[1] * n[2];
+    auto for_sub_cells = [&](int64_t c, auto visit) {   // visit(fine index, triangle id) for every listed pair of parent c
+        const int64_t cz = c % n[2], cy = (c / n[2]) % n[1], cx = c / (n[1] * n[2]);
+        const int2 r = cells[(size_t)c];
+        for (int sx = 0; sx < k[0]; ++sx)
+            for (int sy = 0; sy < k[1]; ++sy)
+                for (int sz = 0; sz < k[2]; ++sz) {
+                    const int64_t fx = cx * k[0] + sx, fy = cy * k[1] + sy, fz = cz * k[2] + sz;
+                    const double lo[3] = {fb[0][(size_t)fx], fb[1][(size_t)fy], fb[2][(size_t)fz]};
+                    const double hi[3] = {fb[0][(size_t)fx + 1], fb[1][(size_t)fy + 1], fb[2][(size_t)fz + 1]};
+                    const int64_t fi = (fx * nf[1] + fy) * nf[2] + fz;
+                    for (int i = r.x; i < r.y; ++i) {
+                        const int t = tri_idx[(size_t)i];
+                        const double *b = &tb[(size_t)t * 6];
+                        if (b[0] <= hi[0] && b[3] >= lo[0] && b[1] <= hi[1] && b[4] >= lo[1] && b[2] <= hi[2] && b[5] >= lo[2])
+                            visit(fi, t);
+                    }
+                }
+    };
+    parallel_ranges(n_fine, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; ++i) fcells[(size_t)i] = make_int2(0, 0);
+    });
+    parallel_ranges(n_coarse, [&](int64_t c0, int64_t c1) {
+        for (int64_t c = c0; c < c1; ++c) for_sub_cells(c, [&](int64_t fi, int) { ++fcells[(size_t)fi].y; });
+    });
+    int64_t total = 0;
+    for (int64_t i = 0; i < n_fine; ++i) {
+        const int cnt = fcells[(size_t)i].y;
+        if (total + cnt > 0x7fffffffLL) return fail(DSB_EINVAL, "mesh: refined search grid too large");
+        fcells[(size_t)i] = make_int2((int)total, (int)total);   // .y is the fill cursor of the next pass
+        total += cnt;
+    }
+    HostBuf<uint4> fentry((size_t)total + 1);
+    if (!fentry.ok()) return fail(DSB_ENOMEM, "mesh: no page-locked host memory for the search grid");
+    parallel_ranges(n_coarse, [&](int64_t c0, int64_t c1) {   // (a sub-cell belongs to one parent: no two threads share a cursor)
+        for (int64_t c = c0; c < c1; ++c)
+            for_sub_cells(c, [&](int64_t fi, int t) { fentry[(size_t)fcells[(size_t)fi].y++] = box[(size_t)t]; });
+    });
+    fentry[(size_t)total] = make_uint4(0u, 0u, 0u, 0u);
+    DSB_CUDA(cache_malloc(&mb.f_entry, fentry.size() * sizeof(uint4)));
+    DSB_CUDA(cache_malloc(&mb.f_cell_rng, fcells.size() * sizeof(int2)));
+    DSB_CUDA(cache_malloc(&mb.f_xs, fb[0].size() * sizeof(double)));
+    DSB_CUDA(cache_malloc(&mb.f_ys, fb[1].size() * sizeof(double)));
+    DSB_CUDA(cache_malloc(&mb.f_zs, fb[2].size() * sizeof(double)));
+    DSB_CUDA(cudaMemcpy(mb.f_entry, fentry.data(), fentry.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaMemcpy(mb.f_cell_rng, fcells.data(), fcells.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaMemcpy(mb.f_xs, fb[0].data(), fb[0].size() * sizeof(double), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaMemcpy(mb.f_ys, fb[1].data(), fb[1].size() * sizeof(double), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaMemcpy(mb.f_zs, fb[2].data(), fb[2].size() * sizeof(double), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaDeviceSynchronize());  // (pageable sources, see upload_mesh)
+    dsb::SearchGrid &g = mb.dev.fine;
+    g.entry = mb.f_entry;
+    g.cell_rng = mb.f_cell_rng;
+    g.xs = mb.f_xs;
+    g.ys = mb.f_ys;
+    g.zs = mb.f_zs;
+    g.len_xs = (int)nf[0] + 1;
+    g.len_ys = (int)nf[1] + 1;
+    g.len_zs = (int)nf[2] + 1;
+    g.nsv1 = (int)nf[1];
+    g.nsv2 = (int)nf[2];
+    g.inv_hx = nf[0] / (grid[0][n[0]] - grid[0][0]);
+    g.inv_hy = nf[1] / (grid[1][n[1]] - grid[1][0]);
+    g.inv_hz = nf[2] / (grid[2][n[2]] - grid[2][0]);
+    for (int a = 0; a < 3; ++a) mb.refine[a] = k[a];
+    return DSB_OK;
+}
+
+int upload_mesh(const dsb_mesh &m, MeshBuffers &mb, double step_l = 0.0)
 {
     Range nvtx("dsb: mesh re-layout + upload");
     if (!m.vertices || !m.faces || !m.xs || !m.ys || !m.zs || !m.subvoxel_indices ||
@@ -530,6 +690,28 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb)
         d.qscale[k] = 32767.0 / d.top[k];
     }
     d.perm_prob = m.perm_prob;
+    // the grid the cooperative search walks: the reference grid itself ...
+    d.fine.entry = mb.entry;
+    d.fine.cell_rng = mb.cell_rng;
+    d.fine.xs = mb.xs;
+    d.fine.ys = mb.ys;
+    d.fine.zs = mb.zs;
+    d.fine.len_xs = d.len_xs;
+    d.fine.len_ys = d.len_ys;
+    d.fine.len_zs = d.len_zs;
+    d.fine.nsv1 = d.nsv1;
+    d.fine.nsv2 = d.nsv2;
+    d.fine.inv_hx = d.inv_hx;
+    d.fine.inv_hy = d.inv_hy;
+    d.fine.inv_hz = d.inv_hz;
+    for (int k = 0; k < 3; ++k) d.fine.margin[k] = 1e-11 * d.vox[k];
+    // ... or a refinement of it
+    int refine[3];
+    choose_refinement(m, step_l, m.n_triangle_indices, refine);
+    if (refine[0] * refine[1] * refine[2] > 1) {
+        int rc = build_search_grid(m, cells, tri_idx, box, refine, mb);
+        if (rc) return rc;
+    }
     mb.h_cells = std::move(cells);
     mb.h_tri_idx = std::move(tri_idx);
     mb.h_box = std::move(box);
@@ -686,7 +868,7 @@ void launch_walk(const dsb::KParams &kp, int grid, cudaStream_t st)
     if constexpr (SUB == 4) {
         // a step shorter than the smallest grid spacing overlaps at most 2 cells per axis: the
         // kernel variant with 8 cell slots per walker does the same work with shorter loops
-        const dsb::MeshDev &g = kp.mesh;
+        const dsb::SearchGrid &g = kp.mesh.fine;
         const double h_min = 1.0 / std::max(g.inv_hx, std::max(g.inv_hy, g.inv_hz));
         if (kp.step_l < h_min) {
             launch_walk_cells<4, dsb::kMaxCellsShortStep>(kp, grid, st);
@@ -944,7 +1126,7 @@ static int create_impl(const dsb_params *params, const double *gradient, dsb_sim
     DSB_TRY(cudaStreamSynchronize(s->stream));  // the sources (caller's gradient, lr_u, lr_v) are free again
 #undef DSB_TRY
     if (params->substrate == DSB_MESH) {
-        rc = upload_mesh(params->mesh, s->mesh);
+        rc = upload_mesh(params->mesh, s->mesh, params->step_l);
         if (rc) {
             std::string keep = g_err;
             dsb_destroy(s), *live = nullptr;

@@ -37,6 +37,19 @@ __host__ __device__ constexpr int grad_row_len(int chunk) { return 3 * chunk + 4
 #endif
 constexpr int kGradRows = DSB_GRADROWS;  // measurements per gradient tile staged in shared memory (a multiple of 8)
 
+// The grid the cooperative collision search walks: the reference's subvoxel grid, or a refinement of
+// it (every cell cut into kx x ky x kz sub-cells whose lists hold the parent's triangles that reach
+// into the sub-cell).  Same layout as the reference grid's arrays in MeshDev.
+struct SearchGrid {
+    const uint4 *entry;     // per list entry: triangle id + box, as MeshDev::entry
+    const int2 *cell_rng;   // (cells,) [begin, end) into entry
+    const double *xs, *ys, *zs;
+    int len_xs, len_ys, len_zs;
+    int nsv1, nsv2;
+    double inv_hx, inv_hy, inv_hz;  // guesses only
+    double margin[3];   // a segment end closer than this to a cell boundary sends its walker to the per-lane search
+};
+
 struct MeshDev {
     const double *tri;      // (n_faces, kTriStride): A, B-A, C-A, pad
     const int *tri_idx;     // (K,) triangle ids, cell after cell (reference order)
@@ -52,6 +65,7 @@ struct MeshDev {
     double top[3];      // xs[-1], ys[-1], zs[-1]: the image shift unit (simulations.py:943)
     double qscale[3];   // 32767 / top: the 15-bit grid of the box filter
     double perm_prob;
+    SearchGrid fine;    // what mesh_closest_hit walks (the arrays above when the grid is not refined)
 };
 
 struct KParams {
@@ -260,8 +274,8 @@ __device__ __forceinline__ void axis_cell(const AxisCells &r, int n, long long k
 // period index is unambiguous.  Then both _ll_ and _ul_subvoxel_overlap_periodic follow from the
 // cell (ll = its global index, ul = that + 1).  Returns false when x is on (or within rounding
 // of) a cell or period boundary; the caller then uses the generic lookups above.
-__device__ __forceinline__ bool cell_of(const double *xs, int n, double V, double invV, double inv_h, double x,
-                                        int &cell, int &image)
+__device__ __forceinline__ bool cell_of(const double *xs, int n, double V, double invV, double inv_h, double margin,
+                                        double x, int &cell, int &image)
 {
     const double q = x * invV;
     const double fl = floor(q);
@@ -271,7 +285,7 @@ __device__ __forceinline__ bool cell_of(const double *xs, int n, double V, doubl
     const double lo = __ldg(xs + c), hi = __ldg(xs + c + 1);
     cell = c;
     image = __double2int_rz(fl);
-    return fr > 1e-9 && fr < 1.0 - 1e-9 && fabs(q) < 1e5 && lo < sh && sh < hi;
+    return fr > 1e-9 && fr < 1.0 - 1e-9 && fabs(q) < 1e5 && sh - lo > margin && hi - sh > margin;
 }
 
 struct AxisSpan {
@@ -286,12 +300,12 @@ struct AxisSpan {
 constexpr int kMaxSpan = DSB_SPAN;  // cells per axis the cooperative search takes
 
 // cells overlapped by [a, b] (a = walker, b = end of the remaining step) along one axis
-__device__ __forceinline__ bool axis_span(const double *xs, int n, double V, double invV, double inv_h, double a,
-                                          double b, AxisSpan &sp)
+__device__ __forceinline__ bool axis_span(const double *xs, int n, double V, double invV, double inv_h, double margin,
+                                          double a, double b, AxisSpan &sp)
 {
     int ca, ia, cb, ib;
-    const bool oka = cell_of(xs, n, V, invV, inv_h, a, ca, ia);
-    const bool okb = cell_of(xs, n, V, invV, inv_h, b, cb, ib);
+    const bool oka = cell_of(xs, n, V, invV, inv_h, margin, a, ca, ia);
+    const bool okb = cell_of(xs, n, V, invV, inv_h, margin, b, cb, ib);
     const bool a_first = !(b < a);
     sp.cell = a_first ? ca : cb;
     sp.image = a_first ? ia : ib;
@@ -314,15 +328,15 @@ struct MeshScratch {
     double dir[3][32];     // unit step of each lane's walker
     double org[3][2][32];  // its position moved into the base voxel: image of the first cell, next image
     unsigned long long best_d[32];  // closest hit distance per walker (bit pattern of a positive double)
-    unsigned best_key[32];          // visiting-order number of the first triangle at that distance
-    int best_tri[32];               // that triangle
+    int best_tri[32];               // smallest ...
+    int best_tri_hi[32];            // ... and largest id among the triangles at that distance (different: a tie)
     union {                         // (the hit distances are written after the last use of the boxes)
-        uint4 range_box[kRangeCap];     // segment box for the filter (3 words); owner lane | image flags << 8 | order << 16
+        uint4 range_box[kRangeCap];     // segment box for the filter (3 words); owner lane | image flags << 8
         double hit[kSurvivorCap];       // distance found for the survivor (inf: none)
     };
     int2 range_pos[kRangeCap];      // number of the range's first entry in the warp's flat numbering; its place in the list
     unsigned start_bits[kEntryCap / 32 + 1];    // bit j: a range starts at flat entry j (+ a word of padding)
-    unsigned long long survivor[kSurvivorCap];  // triangle (32) | owner lane (8) | image flags (3) << 8 | order (16) << 16
+    unsigned long long survivor[kSurvivorCap];  // triangle (32) | owner lane (8) | image flags (3) << 8
 };
 static_assert(kSurvivorCap * sizeof(double) <= kRangeCap * sizeof(uint4), "hit[] must fit over range_box[]");
 
@@ -347,7 +361,7 @@ struct CellWalk {
         iy = wy ? 0 : iy;
         ix += wy;
     }
-    __device__ __forceinline__ int index(const MeshDev &g, const AxisSpan &sx, const AxisSpan &sy, const AxisSpan &sz,
+    __device__ __forceinline__ int index(const SearchGrid &g, const AxisSpan &sx, const AxisSpan &sy, const AxisSpan &sz,
                                          int &flags) const
     {
         int cx = sx.cell + ix, cy = sy.cell + iy, cz = sz.cell + iz;
@@ -411,6 +425,17 @@ __device__ __noinline__ void mesh_closest_hit_alone(const MeshDev &g, const Vec3
 // filter only ever errs on the side of keeping a triangle).  The lists of all 32 walkers are
 // numbered through and filtered 32 entries at a time (coalesced), the survivors are compacted
 // (ballot) and tested exactly, again 32 at a time.
+//
+// The lists that are filtered are those of g.fine: the reference's grid, or a refinement of it whose
+// sub-cell lists hold the parent cell's triangles that reach into the sub-cell (padded boxes, built
+// at upload).  The sub-cells the segment overlaps lie inside the reference cells it overlaps, and
+// their lists are subsets of the parents', so only triangles the reference tests are tested; and a
+// triangle the reference hits within the remaining length is hit at a point of the segment, which
+// lies in an overlapped sub-cell the triangle reaches into (the segment's ends keep a margin from
+// the cell boundaries, else the walker searches alone), so it is tested.  Shorter lists, same hit.
+// What the sub-cells do not preserve is the reference's visiting order, which decides between
+// DIFFERENT triangles hit at bitwise the same distance (a ray through a shared edge): such a walker
+// repeats its search alone with the reference's own loops.
 template <int MAXC>
 __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &sc, const int lane, const bool need,
                                                  const Vec3 &pos, const Vec3 &s, const double step_l,
@@ -418,13 +443,15 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
 {
     const unsigned full = 0xffffffffu;
     const double inf = __longlong_as_double(0x7FF0000000000000LL);
+    const SearchGrid &f = g.fine;
     min_d = inf;
     bool fast = false;
     AxisSpan sx = {0, 0, 0}, sy = {0, 0, 0}, sz = {0, 0, 0};
     double ex = 0.0, ey = 0.0, ez = 0.0;
     int n_ranges = 0, n_entries = 0, n_cells = 0;
     sc.best_d[lane] = 0x7FF0000000000000ULL;
-    sc.best_key[lane] = 0xffffffffu;
+    sc.best_tri[lane] = 0x7fffffff;
+    sc.best_tri_hi[lane] = -1;
 #pragma unroll
     for (int k = 0; k < kEntryCap / 1024; ++k) sc.start_bits[lane + 32 * k] = 0u;
     if (need) {
@@ -433,9 +460,9 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         ex = add_(pos.x, mul_(step_l, s.x));
         ey = fma_(step_l, s.y, pos.y);
         ez = fma_(step_l, s.z, pos.z);
-        fast = axis_span(g.xs, g.len_xs - 1, g.vox[0], g.inv_vox[0], g.inv_hx, pos.x, ex, sx);
-        fast &= axis_span(g.ys, g.len_ys - 1, g.vox[1], g.inv_vox[1], g.inv_hy, pos.y, ey, sy);
-        fast &= axis_span(g.zs, g.len_zs - 1, g.vox[2], g.inv_vox[2], g.inv_hz, pos.z, ez, sz);
+        fast = axis_span(f.xs, f.len_xs - 1, g.vox[0], g.inv_vox[0], f.inv_hx, f.margin[0], pos.x, ex, sx);
+        fast &= axis_span(f.ys, f.len_ys - 1, g.vox[1], g.inv_vox[1], f.inv_hy, f.margin[1], pos.y, ey, sy);
+        fast &= axis_span(f.zs, f.len_zs - 1, g.vox[2], g.inv_vox[2], f.inv_hz, f.margin[2], pos.z, ez, sz);
         n_cells = sx.count * sy.count * sz.count;
         fast = fast && n_cells <= MAXC;
         if constexpr (MAXC == kMaxCellsShortStep) fast = fast && sx.count <= 2 && sy.count <= 2 && sz.count <= 2;
@@ -453,15 +480,15 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
     if constexpr (MAXC == kMaxCellsShortStep) {
         if (fast) {
             int c1 = sx.cell + 1;
-            wrap_x = c1 >= g.len_xs - 1;
-            off_x[0] = sx.cell * g.nsv1 * g.nsv2;
-            off_x[1] = (wrap_x ? 0 : c1) * g.nsv1 * g.nsv2;
+            wrap_x = c1 >= f.len_xs - 1;
+            off_x[0] = sx.cell * f.nsv1 * f.nsv2;
+            off_x[1] = (wrap_x ? 0 : c1) * f.nsv1 * f.nsv2;
             c1 = sy.cell + 1;
-            wrap_y = c1 >= g.len_ys - 1;
-            off_y[0] = sy.cell * g.nsv2;
-            off_y[1] = (wrap_y ? 0 : c1) * g.nsv2;
+            wrap_y = c1 >= f.len_ys - 1;
+            off_y[0] = sy.cell * f.nsv2;
+            off_y[1] = (wrap_y ? 0 : c1) * f.nsv2;
             c1 = sz.cell + 1;
-            wrap_z = c1 >= g.len_zs - 1;
+            wrap_z = c1 >= f.len_zs - 1;
             off_z[0] = sz.cell;
             off_z[1] = wrap_z ? 0 : c1;
         }
@@ -469,7 +496,7 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         for (int c = 0; c < 8; ++c) {
             const int ix = c >> 2, iy = (c >> 1) & 1, iz = c & 1;
             if (fast && ix < sx.count && iy < sy.count && iz < sz.count)
-                rng[c] = __ldg(g.cell_rng + off_x[ix] + off_y[iy] + off_z[iz]);
+                rng[c] = __ldg(f.cell_rng + off_x[ix] + off_y[iy] + off_z[iz]);
         }
     } else {
         // general spans: the loops stop at the largest cell count of the warp
@@ -480,7 +507,7 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
             if (c >= n_cells_warp) break;
             if (fast && c < n_cells) {
                 int flags;
-                rng[c] = __ldg(g.cell_rng + cw.index(g, sx, sy, sz, flags));
+                rng[c] = __ldg(f.cell_rng + cw.index(f, sx, sy, sz, flags));
             }
             cw.next(sy, sz);
         }
@@ -535,8 +562,7 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
                 sc.range_box[k] = make_uint4(((fx ? hx[1] : hx[0]) | ((fy ? hy[1] : hy[0]) << 16)) + kSwarH,
                                              ((fz ? hz[1] : hz[0]) | ((fx ? lx[1] : lx[0]) << 16)) + kSwarH,
                                              ((fy ? ly[1] : ly[0]) | ((fz ? lz[1] : lz[0]) << 16)) + kSwarH,
-                                             (unsigned)lane | ((unsigned)flags << 8) |
-                                                 ((unsigned)(first - (incl_e - n_entries)) << 16));
+                                             (unsigned)lane | ((unsigned)flags << 8));
                 sc.range_pos[k] = make_int2(first, rng[c].x);
                 atomicOr(&sc.start_bits[first >> 5], 1u << (first & 31));
                 ++k;
@@ -553,7 +579,7 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
             for (int c = 0; c < MAXC; ++c) {
                 if (c >= n_cells_warp) break;
                 int flags;
-                cw.index(g, sx, sy, sz, flags);
+                cw.index(f, sx, sy, sz, flags);
                 add_range(c, flags);
                 cw.next(sy, sz);
             }
@@ -581,13 +607,13 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
                 a[h] = sc.range_box[r];
                 const int2 rp = sc.range_pos[r];
                 off[h] = j - rp.x;
-                b[h] = __ldg(g.entry + rp.y + off[h]);
+                b[h] = __ldg(f.entry + rp.y + off[h]);
             }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             pass[h] = ((a[h].x - b[h].y) & (a[h].y - b[h].z) & (a[h].z - b[h].w) & kSwarH) == kSwarH;
-            rec[h] = (unsigned long long)b[h].x | ((unsigned long long)(a[h].w + ((unsigned)off[h] << 16)) << 32);
+            rec[h] = (unsigned long long)b[h].x | ((unsigned long long)a[h].w << 32);
             const unsigned m = __ballot_sync(full, pass[h]);
             if (pass[h]) {
                 const int k = n_surv + __popc(m & ((1u << lane) - 1u));
@@ -617,31 +643,28 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         if (is_hit) atomicMin(&sc.best_d[owner], (unsigned long long)__double_as_longlong(t));
     }
     __syncwarp();
-    // equal distances (a ray through a shared edge): the triangle visited first wins
-    for (int j = lane; j < n_surv; j += 32) {
-        const unsigned hi = (unsigned)(sc.survivor[j] >> 32);
-        const double t = sc.hit[j];
-        if (t < inf && (unsigned long long)__double_as_longlong(t) == sc.best_d[hi & 0xff])
-            atomicMin(&sc.best_key[hi & 0xff], hi >> 16);
-    }
-    __syncwarp();
+    // which triangle: the one at the closest distance; two different triangles at bitwise the same
+    // distance (a ray through a shared edge) are a tie the reference breaks by its visiting order
     for (int j = lane; j < n_surv; j += 32) {
         const unsigned long long w = sc.survivor[j];
-        const unsigned hi = (unsigned)(w >> 32);
+        const int owner = (unsigned)(w >> 32) & 0xff;
         const double t = sc.hit[j];
-        if (t < inf && (unsigned long long)__double_as_longlong(t) == sc.best_d[hi & 0xff] &&
-            (hi >> 16) == sc.best_key[hi & 0xff])
-            sc.best_tri[hi & 0xff] = (int)((unsigned)w & kEntryTriMask);
+        if (t < inf && (unsigned long long)__double_as_longlong(t) == sc.best_d[owner]) {
+            const int id = (int)((unsigned)w & kEntryTriMask);
+            atomicMin(&sc.best_tri[owner], id);
+            atomicMax(&sc.best_tri_hi[owner], id);
+        }
     }
     __syncwarp();
 
-    if (coop && !overflow) {
+    const bool tie = coop && !overflow && sc.best_tri_hi[lane] > sc.best_tri[lane];
+    if (coop && !overflow && !tie) {
         const double d = __longlong_as_double((long long)sc.best_d[lane]);
         if (d < inf) {
             min_d = d;
             closest = sc.best_tri[lane];
         }
-    } else if (need) {  // boundary cases, long segments, table overflow: this lane walks its own cells
+    } else if (need) {  // boundary cases, long segments, table overflow, ties: this lane walks its own cells
         mesh_closest_hit_alone(g, pos, s, ex, ey, ez, min_d, closest);
     }
 }
@@ -822,6 +845,12 @@ struct ParkFlush {
     static constexpr int value = SUB == 3 ? DSB_PARK_ELLIPSOID : DSB_PARK;
 };
 
+#ifndef DSB_A_GLOBAL
+#define DSB_A_GLOBAL 0  // many-measurement kernels of the analytic substrates: gradient (A) fragments by __ldg instead of TMA tiles
+#endif
+#ifndef DSB_B_REGS
+#define DSB_B_REGS 0   // many-measurement kernels: positions of the chunk (B fragments) held in registers, two passes
+#endif
 // D = A * B + C on the FP64 tensor cores: A 8x4 (row major), B 4x8 (column major), C/D 8x8.
 // Lane l holds A[l / 4][l % 4], B[l % 4][l / 4] and C[l / 4][2 * (l % 4) + {0, 1}].
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
@@ -967,6 +996,8 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
         // (phases for n_meas > 4 agree to ~1e-13, not bit for bit; positions are not affected).
         // The ragged end of a run (fewer than C steps) uses the reference's formula.
         constexpr int C = ChunkSteps<SUB>::value, kRows = 3 * C, kRowLen = grad_row_len(C);
+        constexpr bool kBRegs = DSB_B_REGS != 0;
+        constexpr bool kAGlobal = SUB == 4 || DSB_A_GLOBAL != 0;  // A fragments straight from the chunk-major copy in L1/L2
         // a run that starts with a whole chunk starts its accumulators at zero instead of reading
         // zeros it would have had to write first
         const bool first_chunk_whole = p.t0 == 0 && p.t1 >= C;
@@ -1001,7 +1032,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        if (SUB != 4 && threadIdx.x == 0 && p.t0 % C == 0 && p.t1 - p.t0 >= C)  // first tile of the first chunk
+        if (!kAGlobal && threadIdx.x == 0 && p.t0 % C == 0 && p.t1 - p.t0 >= C)  // first tile of the first chunk
             tma_load_1d(s_grad, p.grad_chunked + (long long)(p.t0 / C) * p.n_meas * kRowLen,
                         min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[0]);
         for (int t = p.t0; t < p.t1; t += C) {
@@ -1042,66 +1073,147 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                 };
                 // B fragment of k-step q and walker tile j: row 4q + t4 (so row & 3 == t4 for every q),
                 // column 8j + g8 -> one pointer per j, the k-step is an immediate offset
-                const double *bcol[4];
+                if constexpr (kBRegs) {
+                    // The chunk's positions of 16 walkers (two 8-walker tiles) stay in registers while all
+                    // measurements pass by: the B fragments are read from shared memory once per pass
+                    // instead of once per 8 measurements (0.54 instead of 1.25 shared-memory loads per
+                    // mma; shared-memory operand delivery was the top stall of this loop).  Two passes per
+                    // chunk, one per half of the warp's walkers; the gradient tiles are streamed once per
+                    // pass.
+                    constexpr int kQ = kRows / 4;
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        double B[kQ][2];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) bcol[j] = xs + t4 * 32 + ((8 * j + g8) ^ (t4 << 3));
-                double c[4][2], c_next[4][2];
-                load_c(0, c_next);
-                for (int m0 = 0; m0 < p.n_meas; m0 += 8) {
-                    if (SUB != 4 && m0 % kGradRows == 0) {  // next tile
-                        const int bufi = n_tiles & 1;
-                        __syncthreads();  // everybody is done with the other buffer
-                        if (threadIdx.x == 0) {
-                            const int m_next = m0 + kGradRows;
-                            if (m_next < p.n_meas)
-                                tma_load_1d(s_grad + (bufi ^ 1) * kGradRows * kRowLen, gc + (long long)m_next * kRowLen,
-                                            min(kGradRows, p.n_meas - m_next) * kRowLen * 8, &s_bar[bufi ^ 1]);
-                            else if (next_chunk)
-                                tma_load_1d(s_grad + (bufi ^ 1) * kGradRows * kRowLen, gc + (long long)p.n_meas * kRowLen,
-                                            min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[bufi ^ 1]);
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const double *bc = xs + t4 * 32 + ((8 * (2 * half + jj) + g8) ^ (t4 << 3));
+#pragma unroll
+                            for (int q = 0; q < kQ; ++q) B[q][jj] = bc[128 * q];
                         }
-                        mbar_wait(&s_bar[bufi], (n_tiles >> 1) & 1);
-                        tile = s_grad + bufi * kGradRows * kRowLen;
-                        ++n_tiles;
-                    }
+                        auto load_c2 = [&](int m0, double (&c)[2][2]) {
+                            const int m = m0 + g8;
+                            const bool row_ok = m < p.n_meas && !(first_chunk_whole && t == 0);
+                            const double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        c[j][0] = c_next[j][0];
-                        c[j][1] = c_next[j][1];
-                    }
-                    if (m0 + 8 < p.n_meas) load_c(m0 + 8, c_next);
-                    const int m = m0 + g8;  // the measurement of this lane's A and C fragments
-                    const bool row_ok = m < p.n_meas;
-                    double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
-                    // The warps of a mesh block reach this pass at different times (their walks differ),
-                    // so they do not share gradient tiles (that needs block-wide barriers): each reads
-                    // its A fragments from the L1/L2-resident chunk-major copy directly.
-                    const double *arow = SUB == 4 ? gc + (long long)(row_ok ? m : 0) * kRowLen + t4
-                                                  : tile + ((m0 % kGradRows) + g8) * kRowLen + t4;
-                    // operands of k-step q + 1 are read from shared memory while the four products of
-                    // k-step q run
-                    double a = row_ok ? (SUB == 4 ? __ldg(arow) : arow[0]) : 0.0, b[4];
+                            for (int jj = 0; jj < 2; ++jj) {
+                                const int j = 2 * half + jj;
+                                const long long wj = w_warp + 8 * j + 2 * t4;
+                                c[jj][0] = (row_ok && wj < p.w_end) ? __ldcs(row + 8 * j) : 0.0;
+                                c[jj][1] = (row_ok && wj + 1 < p.w_end) ? __ldcs(row + 8 * j + 1) : 0.0;
+                            }
+                        };
+                        double c[2][2], c_next[2][2];
+                        load_c2(0, c_next);
+                        for (int m0 = 0; m0 < p.n_meas; m0 += 8) {
+                            if (!kAGlobal && m0 % kGradRows == 0) {  // next tile
+                                const int bufi = n_tiles & 1;
+                                __syncthreads();  // everybody is done with the other buffer
+                                if (threadIdx.x == 0) {
+                                    const int m_next = m0 + kGradRows;
+                                    double *dst = s_grad + (bufi ^ 1) * kGradRows * kRowLen;
+                                    if (m_next < p.n_meas)
+                                        tma_load_1d(dst, gc + (long long)m_next * kRowLen,
+                                                    min(kGradRows, p.n_meas - m_next) * kRowLen * 8, &s_bar[bufi ^ 1]);
+                                    else if (half == 0)   // the same chunk again for the other half of the walkers
+                                        tma_load_1d(dst, gc, min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[bufi ^ 1]);
+                                    else if (next_chunk)
+                                        tma_load_1d(dst, gc + (long long)p.n_meas * kRowLen, min(kGradRows, p.n_meas) * kRowLen * 8,
+                                                    &s_bar[bufi ^ 1]);
+                                }
+                                mbar_wait(&s_bar[bufi], (n_tiles >> 1) & 1);
+                                tile = s_grad + bufi * kGradRows * kRowLen;
+                                ++n_tiles;
+                            }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) b[j] = bcol[j][0];
+                            for (int jj = 0; jj < 2; ++jj) {
+                                c[jj][0] = c_next[jj][0];
+                                c[jj][1] = c_next[jj][1];
+                            }
+                            if (m0 + 8 < p.n_meas) load_c2(m0 + 8, c_next);
+                            const int m = m0 + g8;  // the measurement of this lane's A and C fragments
+                            const bool row_ok = m < p.n_meas;
+                            double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
+                            const double *arow = kAGlobal ? gc + (long long)(row_ok ? m : 0) * kRowLen + t4
+                                                          : tile + ((m0 % kGradRows) + g8) * kRowLen + t4;
+                            double a[kQ];
 #pragma unroll
-                    for (int q = 0; q < kRows / 4; ++q) {
-                        double a_next = 0.0, b_next[4] = {0.0, 0.0, 0.0, 0.0};
-                        if (q + 1 < kRows / 4) {
-                            a_next = row_ok ? (SUB == 4 ? __ldg(arow + 4 * (q + 1)) : arow[4 * (q + 1)]) : 0.0;
+                            for (int q = 0; q < kQ; ++q) a[q] = row_ok ? (kAGlobal ? __ldg(arow + 4 * q) : arow[4 * q]) : 0.0;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) b_next[j] = bcol[j][128 * (q + 1)];
+                            for (int q = 0; q < kQ; ++q) {
+                                dmma_m8n8k4(c[0][0], c[0][1], a[q], B[q][0]);
+                                dmma_m8n8k4(c[1][0], c[1][1], a[q], B[q][1]);
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < 2; ++jj) {
+                                const int j = 2 * half + jj;
+                                const long long wj = w_warp + 8 * j + 2 * t4;
+                                if (row_ok && wj < p.w_end) __stcs(row + 8 * j, c[jj][0]);
+                                if (row_ok && wj + 1 < p.w_end) __stcs(row + 8 * j + 1, c[jj][1]);
+                            }
                         }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) dmma_m8n8k4(c[j][0], c[j][1], a, b[j]);
-                        a = a_next;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) b[j] = b_next[j];
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const long long wj = w_warp + 8 * j + 2 * t4;
-                        if (row_ok && wj < p.w_end) __stcs(row + 8 * j, c[j][0]);
-                        if (row_ok && wj + 1 < p.w_end) __stcs(row + 8 * j + 1, c[j][1]);
+                } else {
+                    const double *bcol[4];
+    #pragma unroll
+                    for (int j = 0; j < 4; ++j) bcol[j] = xs + t4 * 32 + ((8 * j + g8) ^ (t4 << 3));
+                    double c[4][2], c_next[4][2];
+                    load_c(0, c_next);
+                    for (int m0 = 0; m0 < p.n_meas; m0 += 8) {
+                        if (!kAGlobal && m0 % kGradRows == 0) {  // next tile
+                            const int bufi = n_tiles & 1;
+                            __syncthreads();  // everybody is done with the other buffer
+                            if (threadIdx.x == 0) {
+                                const int m_next = m0 + kGradRows;
+                                if (m_next < p.n_meas)
+                                    tma_load_1d(s_grad + (bufi ^ 1) * kGradRows * kRowLen, gc + (long long)m_next * kRowLen,
+                                                min(kGradRows, p.n_meas - m_next) * kRowLen * 8, &s_bar[bufi ^ 1]);
+                                else if (next_chunk)
+                                    tma_load_1d(s_grad + (bufi ^ 1) * kGradRows * kRowLen, gc + (long long)p.n_meas * kRowLen,
+                                                min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[bufi ^ 1]);
+                            }
+                            mbar_wait(&s_bar[bufi], (n_tiles >> 1) & 1);
+                            tile = s_grad + bufi * kGradRows * kRowLen;
+                            ++n_tiles;
+                        }
+    #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            c[j][0] = c_next[j][0];
+                            c[j][1] = c_next[j][1];
+                        }
+                        if (m0 + 8 < p.n_meas) load_c(m0 + 8, c_next);
+                        const int m = m0 + g8;  // the measurement of this lane's A and C fragments
+                        const bool row_ok = m < p.n_meas;
+                        double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
+                        // The warps of a mesh block reach this pass at different times (their walks differ),
+                        // so they do not share gradient tiles (that needs block-wide barriers): each reads
+                        // its A fragments from the L1/L2-resident chunk-major copy directly.
+                        const double *arow = kAGlobal ? gc + (long long)(row_ok ? m : 0) * kRowLen + t4
+                                                      : tile + ((m0 % kGradRows) + g8) * kRowLen + t4;
+                        // operands of k-step q + 1 are read from shared memory while the four products of
+                        // k-step q run
+                        double a = row_ok ? (kAGlobal ? __ldg(arow) : arow[0]) : 0.0, b[4];
+    #pragma unroll
+                        for (int j = 0; j < 4; ++j) b[j] = bcol[j][0];
+    #pragma unroll
+                        for (int q = 0; q < kRows / 4; ++q) {
+                            double a_next = 0.0, b_next[4] = {0.0, 0.0, 0.0, 0.0};
+                            if (q + 1 < kRows / 4) {
+                                a_next = row_ok ? (kAGlobal ? __ldg(arow + 4 * (q + 1)) : arow[4 * (q + 1)]) : 0.0;
+    #pragma unroll
+                                for (int j = 0; j < 4; ++j) b_next[j] = bcol[j][128 * (q + 1)];
+                            }
+    #pragma unroll
+                            for (int j = 0; j < 4; ++j) dmma_m8n8k4(c[j][0], c[j][1], a, b[j]);
+                            a = a_next;
+    #pragma unroll
+                            for (int j = 0; j < 4; ++j) b[j] = b_next[j];
+                        }
+    #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const long long wj = w_warp + 8 * j + 2 * t4;
+                            if (row_ok && wj < p.w_end) __stcs(row + 8 * j, c[j][0]);
+                            if (row_ok && wj + 1 < p.w_end) __stcs(row + 8 * j + 1, c[j][1]);
+                        }
                     }
                 }
             } else if (active) {  // ragged end of the run, or a launch that does not start on a chunk boundary

@@ -240,6 +240,12 @@ def part_edges(n_walkers, n_slots=1, part=None):
         return list(range(0, n_walkers, part)) + [n_walkers]
     edges, size = [0], int(os.environ.get("DISIMPY_B200_PART_FIRST", _PART if n_slots == 1 else _PART_FIRST))
     while edges[-1] < n_walkers:
+        left = n_walkers - edges[-1]
+        if left < n_slots * size:
+            # the last round is split evenly: a round-robin deal of equal parts with a ragged end gives one
+            # GPU up to a whole part more than another (measured at 2 GPUs x 1e6 walkers: 1 048 576 against
+            # 951 424 walkers, 204 ms against 192 ms)
+            size = max(128, (left + 128 * n_slots - 1) // (128 * n_slots) * 128)
         for _ in range(n_slots):
             if edges[-1] < n_walkers:
                 edges.append(min(edges[-1] + size, n_walkers))
