@@ -845,12 +845,6 @@ struct ParkFlush {
     static constexpr int value = SUB == 3 ? DSB_PARK_ELLIPSOID : DSB_PARK;
 };
 
-#ifndef DSB_A_GLOBAL
-#define DSB_A_GLOBAL 0  // many-measurement kernels of the analytic substrates: gradient (A) fragments by __ldg instead of TMA tiles
-#endif
-#ifndef DSB_B_REGS
-#define DSB_B_REGS 0   // many-measurement kernels: positions of the chunk (B fragments) held in registers, two passes
-#endif
 // D = A * B + C on the FP64 tensor cores: A 8x4 (row major), B 4x8 (column major), C/D 8x8.
 // Lane l holds A[l / 4][l % 4], B[l % 4][l / 4] and C[l / 4][2 * (l % 4) + {0, 1}].
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
@@ -991,13 +985,14 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
         //    through HBM per chunk.  (Measured in round 2, profiles/r02_c_kbench_variants.txt: with
         //    L2-resident hints -- ld/st.cg, 3 or 4 blocks per SM so that the resident tiles, 82-109 MB
         //    at 180 measurements, fit the 126 MB L2 -- the sphere runs at 1.02e10 walker-steps/s
-        //    against 1.34e10 with evict-first: the tiles of retired blocks crowd out the live ones.)
+        //    against 1.34e10 with evict-first: the tiles of retired blocks crowd out the live ones.
+        //    Also measured without gain (profiles/r02_f_kbench_many_meas_variants.txt): the chunk's B
+        //    fragments held in registers for 16 walkers at a time (0.54 instead of 1.25 shared-memory
+        //    loads per mma, two passes: 1.29e10), A fragments by __ldg instead of TMA tiles (1.28e10).)
         // Summation order and roundings differ from the reference's fma chain at the 1e-16 level
         // (phases for n_meas > 4 agree to ~1e-13, not bit for bit; positions are not affected).
         // The ragged end of a run (fewer than C steps) uses the reference's formula.
         constexpr int C = ChunkSteps<SUB>::value, kRows = 3 * C, kRowLen = grad_row_len(C);
-        constexpr bool kBRegs = DSB_B_REGS != 0;
-        constexpr bool kAGlobal = SUB == 4 || DSB_A_GLOBAL != 0;  // A fragments straight from the chunk-major copy in L1/L2
         // a run that starts with a whole chunk starts its accumulators at zero instead of reading
         // zeros it would have had to write first
         const bool first_chunk_whole = p.t0 == 0 && p.t1 >= C;
@@ -1032,7 +1027,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        if (!kAGlobal && threadIdx.x == 0 && p.t0 % C == 0 && p.t1 - p.t0 >= C)  // first tile of the first chunk
+        if (SUB != 4 && threadIdx.x == 0 && p.t0 % C == 0 && p.t1 - p.t0 >= C)  // first tile of the first chunk
             tma_load_1d(s_grad, p.grad_chunked + (long long)(p.t0 / C) * p.n_meas * kRowLen,
                         min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[0]);
         for (int t = p.t0; t < p.t1; t += C) {
@@ -1073,147 +1068,66 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                 };
                 // B fragment of k-step q and walker tile j: row 4q + t4 (so row & 3 == t4 for every q),
                 // column 8j + g8 -> one pointer per j, the k-step is an immediate offset
-                if constexpr (kBRegs) {
-                    // The chunk's positions of 16 walkers (two 8-walker tiles) stay in registers while all
-                    // measurements pass by: the B fragments are read from shared memory once per pass
-                    // instead of once per 8 measurements (0.54 instead of 1.25 shared-memory loads per
-                    // mma; shared-memory operand delivery was the top stall of this loop).  Two passes per
-                    // chunk, one per half of the warp's walkers; the gradient tiles are streamed once per
-                    // pass.
-                    constexpr int kQ = kRows / 4;
-#pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
-                        double B[kQ][2];
+                const double *bcol[4];
 #pragma unroll
-                        for (int jj = 0; jj < 2; ++jj) {
-                            const double *bc = xs + t4 * 32 + ((8 * (2 * half + jj) + g8) ^ (t4 << 3));
-#pragma unroll
-                            for (int q = 0; q < kQ; ++q) B[q][jj] = bc[128 * q];
+                for (int j = 0; j < 4; ++j) bcol[j] = xs + t4 * 32 + ((8 * j + g8) ^ (t4 << 3));
+                double c[4][2], c_next[4][2];
+                load_c(0, c_next);
+                for (int m0 = 0; m0 < p.n_meas; m0 += 8) {
+                    if (SUB != 4 && m0 % kGradRows == 0) {  // next tile
+                        const int bufi = n_tiles & 1;
+                        __syncthreads();  // everybody is done with the other buffer
+                        if (threadIdx.x == 0) {
+                            const int m_next = m0 + kGradRows;
+                            if (m_next < p.n_meas)
+                                tma_load_1d(s_grad + (bufi ^ 1) * kGradRows * kRowLen, gc + (long long)m_next * kRowLen,
+                                            min(kGradRows, p.n_meas - m_next) * kRowLen * 8, &s_bar[bufi ^ 1]);
+                            else if (next_chunk)
+                                tma_load_1d(s_grad + (bufi ^ 1) * kGradRows * kRowLen, gc + (long long)p.n_meas * kRowLen,
+                                            min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[bufi ^ 1]);
                         }
-                        auto load_c2 = [&](int m0, double (&c)[2][2]) {
-                            const int m = m0 + g8;
-                            const bool row_ok = m < p.n_meas && !(first_chunk_whole && t == 0);
-                            const double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
-#pragma unroll
-                            for (int jj = 0; jj < 2; ++jj) {
-                                const int j = 2 * half + jj;
-                                const long long wj = w_warp + 8 * j + 2 * t4;
-                                c[jj][0] = (row_ok && wj < p.w_end) ? __ldcs(row + 8 * j) : 0.0;
-                                c[jj][1] = (row_ok && wj + 1 < p.w_end) ? __ldcs(row + 8 * j + 1) : 0.0;
-                            }
-                        };
-                        double c[2][2], c_next[2][2];
-                        load_c2(0, c_next);
-                        for (int m0 = 0; m0 < p.n_meas; m0 += 8) {
-                            if (!kAGlobal && m0 % kGradRows == 0) {  // next tile
-                                const int bufi = n_tiles & 1;
-                                __syncthreads();  // everybody is done with the other buffer
-                                if (threadIdx.x == 0) {
-                                    const int m_next = m0 + kGradRows;
-                                    double *dst = s_grad + (bufi ^ 1) * kGradRows * kRowLen;
-                                    if (m_next < p.n_meas)
-                                        tma_load_1d(dst, gc + (long long)m_next * kRowLen,
-                                                    min(kGradRows, p.n_meas - m_next) * kRowLen * 8, &s_bar[bufi ^ 1]);
-                                    else if (half == 0)   // the same chunk again for the other half of the walkers
-                                        tma_load_1d(dst, gc, min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[bufi ^ 1]);
-                                    else if (next_chunk)
-                                        tma_load_1d(dst, gc + (long long)p.n_meas * kRowLen, min(kGradRows, p.n_meas) * kRowLen * 8,
-                                                    &s_bar[bufi ^ 1]);
-                                }
-                                mbar_wait(&s_bar[bufi], (n_tiles >> 1) & 1);
-                                tile = s_grad + bufi * kGradRows * kRowLen;
-                                ++n_tiles;
-                            }
-#pragma unroll
-                            for (int jj = 0; jj < 2; ++jj) {
-                                c[jj][0] = c_next[jj][0];
-                                c[jj][1] = c_next[jj][1];
-                            }
-                            if (m0 + 8 < p.n_meas) load_c2(m0 + 8, c_next);
-                            const int m = m0 + g8;  // the measurement of this lane's A and C fragments
-                            const bool row_ok = m < p.n_meas;
-                            double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
-                            const double *arow = kAGlobal ? gc + (long long)(row_ok ? m : 0) * kRowLen + t4
-                                                          : tile + ((m0 % kGradRows) + g8) * kRowLen + t4;
-                            double a[kQ];
-#pragma unroll
-                            for (int q = 0; q < kQ; ++q) a[q] = row_ok ? (kAGlobal ? __ldg(arow + 4 * q) : arow[4 * q]) : 0.0;
-#pragma unroll
-                            for (int q = 0; q < kQ; ++q) {
-                                dmma_m8n8k4(c[0][0], c[0][1], a[q], B[q][0]);
-                                dmma_m8n8k4(c[1][0], c[1][1], a[q], B[q][1]);
-                            }
-#pragma unroll
-                            for (int jj = 0; jj < 2; ++jj) {
-                                const int j = 2 * half + jj;
-                                const long long wj = w_warp + 8 * j + 2 * t4;
-                                if (row_ok && wj < p.w_end) __stcs(row + 8 * j, c[jj][0]);
-                                if (row_ok && wj + 1 < p.w_end) __stcs(row + 8 * j + 1, c[jj][1]);
-                            }
-                        }
+                        mbar_wait(&s_bar[bufi], (n_tiles >> 1) & 1);
+                        tile = s_grad + bufi * kGradRows * kRowLen;
+                        ++n_tiles;
                     }
-                } else {
-                    const double *bcol[4];
-    #pragma unroll
-                    for (int j = 0; j < 4; ++j) bcol[j] = xs + t4 * 32 + ((8 * j + g8) ^ (t4 << 3));
-                    double c[4][2], c_next[4][2];
-                    load_c(0, c_next);
-                    for (int m0 = 0; m0 < p.n_meas; m0 += 8) {
-                        if (!kAGlobal && m0 % kGradRows == 0) {  // next tile
-                            const int bufi = n_tiles & 1;
-                            __syncthreads();  // everybody is done with the other buffer
-                            if (threadIdx.x == 0) {
-                                const int m_next = m0 + kGradRows;
-                                if (m_next < p.n_meas)
-                                    tma_load_1d(s_grad + (bufi ^ 1) * kGradRows * kRowLen, gc + (long long)m_next * kRowLen,
-                                                min(kGradRows, p.n_meas - m_next) * kRowLen * 8, &s_bar[bufi ^ 1]);
-                                else if (next_chunk)
-                                    tma_load_1d(s_grad + (bufi ^ 1) * kGradRows * kRowLen, gc + (long long)p.n_meas * kRowLen,
-                                                min(kGradRows, p.n_meas) * kRowLen * 8, &s_bar[bufi ^ 1]);
-                            }
-                            mbar_wait(&s_bar[bufi], (n_tiles >> 1) & 1);
-                            tile = s_grad + bufi * kGradRows * kRowLen;
-                            ++n_tiles;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        c[j][0] = c_next[j][0];
+                        c[j][1] = c_next[j][1];
+                    }
+                    if (m0 + 8 < p.n_meas) load_c(m0 + 8, c_next);
+                    const int m = m0 + g8;  // the measurement of this lane's A and C fragments
+                    const bool row_ok = m < p.n_meas;
+                    double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
+                    // The warps of a mesh block reach this pass at different times (their walks differ),
+                    // so they do not share gradient tiles (that needs block-wide barriers): each reads
+                    // its A fragments from the L1/L2-resident chunk-major copy directly.
+                    const double *arow = SUB == 4 ? gc + (long long)(row_ok ? m : 0) * kRowLen + t4
+                                                  : tile + ((m0 % kGradRows) + g8) * kRowLen + t4;
+                    // operands of k-step q + 1 are read from shared memory while the four products of
+                    // k-step q run
+                    double a = row_ok ? (SUB == 4 ? __ldg(arow) : arow[0]) : 0.0, b[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) b[j] = bcol[j][0];
+#pragma unroll
+                    for (int q = 0; q < kRows / 4; ++q) {
+                        double a_next = 0.0, b_next[4] = {0.0, 0.0, 0.0, 0.0};
+                        if (q + 1 < kRows / 4) {
+                            a_next = row_ok ? (SUB == 4 ? __ldg(arow + 4 * (q + 1)) : arow[4 * (q + 1)]) : 0.0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) b_next[j] = bcol[j][128 * (q + 1)];
                         }
-    #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            c[j][0] = c_next[j][0];
-                            c[j][1] = c_next[j][1];
-                        }
-                        if (m0 + 8 < p.n_meas) load_c(m0 + 8, c_next);
-                        const int m = m0 + g8;  // the measurement of this lane's A and C fragments
-                        const bool row_ok = m < p.n_meas;
-                        double *row = p.phases + (long long)(row_ok ? m : 0) * N + w_warp + 2 * t4;
-                        // The warps of a mesh block reach this pass at different times (their walks differ),
-                        // so they do not share gradient tiles (that needs block-wide barriers): each reads
-                        // its A fragments from the L1/L2-resident chunk-major copy directly.
-                        const double *arow = kAGlobal ? gc + (long long)(row_ok ? m : 0) * kRowLen + t4
-                                                      : tile + ((m0 % kGradRows) + g8) * kRowLen + t4;
-                        // operands of k-step q + 1 are read from shared memory while the four products of
-                        // k-step q run
-                        double a = row_ok ? (kAGlobal ? __ldg(arow) : arow[0]) : 0.0, b[4];
-    #pragma unroll
-                        for (int j = 0; j < 4; ++j) b[j] = bcol[j][0];
-    #pragma unroll
-                        for (int q = 0; q < kRows / 4; ++q) {
-                            double a_next = 0.0, b_next[4] = {0.0, 0.0, 0.0, 0.0};
-                            if (q + 1 < kRows / 4) {
-                                a_next = row_ok ? (kAGlobal ? __ldg(arow + 4 * (q + 1)) : arow[4 * (q + 1)]) : 0.0;
-    #pragma unroll
-                                for (int j = 0; j < 4; ++j) b_next[j] = bcol[j][128 * (q + 1)];
-                            }
-    #pragma unroll
-                            for (int j = 0; j < 4; ++j) dmma_m8n8k4(c[j][0], c[j][1], a, b[j]);
-                            a = a_next;
-    #pragma unroll
-                            for (int j = 0; j < 4; ++j) b[j] = b_next[j];
-                        }
-    #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const long long wj = w_warp + 8 * j + 2 * t4;
-                            if (row_ok && wj < p.w_end) __stcs(row + 8 * j, c[j][0]);
-                            if (row_ok && wj + 1 < p.w_end) __stcs(row + 8 * j + 1, c[j][1]);
-                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma_m8n8k4(c[j][0], c[j][1], a, b[j]);
+                        a = a_next;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) b[j] = b_next[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const long long wj = w_warp + 8 * j + 2 * t4;
+                        if (row_ok && wj < p.w_end) __stcs(row + 8 * j, c[j][0]);
+                        if (row_ok && wj + 1 < p.w_end) __stcs(row + 8 * j + 1, c[j][1]);
                     }
                 }
             } else if (active) {  // ragged end of the run, or a launch that does not start on a chunk boundary
@@ -1243,6 +1157,213 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
         p.pos[3 * w + 1] = pos.y;
         p.pos[3 * w + 2] = pos.z;
         reinterpret_cast<ulonglong2 *>(p.rng)[w] = make_ulonglong2(rng.s0, rng.s1);
+    }
+}
+
+// ---------------------------------------------------------------- analytic substrates: walker pool
+
+// Collisions with the wall are rare per walker and step (1-5 %) but not per warp: with one walker
+// per lane the reflection code -- two normalisations, a second distance check, ~340 instructions --
+// runs in 40-75 % of the warp's steps for one or two lanes (round-1 profile: 32 % of the sphere
+// kernel's instructions at 8.6 active lanes).  Here a warp owns 64 walkers whose state lives in
+// shared memory.  A step pass advances one runnable walker per lane (lane l serves walkers l and
+// l + 32, in turn); a walker that hits the wall leaves its step in flight in its slot and joins the
+// warp's queue; once kPoolFlush walkers are queued they are bounced together, one per lane, and
+// either finish their step or stay queued.  Lanes are busy in both kinds of pass, and every walker
+// executes exactly its own sequence of operations (simulations.py:705-875), so trajectories and
+// phases are those of walk_kernel bit for bit.  The price is the walker state's round trip through
+// shared memory every step (~25 instructions) against ~140 saved.
+#ifndef DSB_POOL_FLUSH
+#define DSB_POOL_FLUSH 16
+#endif
+#ifndef DSB_POOL_MIN_BLOCKS
+#define DSB_POOL_MIN_BLOCKS 6
+#endif
+constexpr int kPoolFlush = DSB_POOL_FLUSH;       // queued walkers that trigger a bounce pass
+constexpr int kPoolPerWarp = 64;                 // walkers per warp
+constexpr int kPoolPerBlock = kBlock / 32 * kPoolPerWarp;
+
+// one warp's walkers, structure of arrays (index = slot 0..63)
+template <int MR>
+struct PoolWarp {
+    double pos[3][kPoolPerWarp];   // position between steps; the substrate-frame position r0 of a step in flight
+    double dir[3][kPoolPerWarp];   // unit step of a step in flight
+    double step_l[kPoolPerWarp];   // its remaining length
+    double d[kPoolPerWarp];        // distance to the wall found by its last probe
+    double ph[MR][kPoolPerWarp];
+    ulonglong2 rng[kPoolPerWarp];
+    int t[kPoolPerWarp];           // next time step of the walker
+    int iter[kPoolPerWarp];        // intersection checks made in the step in flight
+    unsigned char state[kPoolPerWarp];   // 0 runnable, 1 step in flight (queued), 2 done (or no walker)
+    unsigned char exc[kPoolPerWarp];
+    unsigned char queue[kPoolPerWarp + 32];
+};
+
+template <int SUB, int MR>
+__global__ void __launch_bounds__(kBlock, DSB_POOL_MIN_BLOCKS) walk_pool_kernel(const __grid_constant__ KParams p)
+{
+    static_assert(SUB >= 1 && SUB <= 3 && MR >= 1 && MR <= kMaxRegMeas, "analytic substrates, phases per walker");
+    extern __shared__ __align__(16) unsigned char s_pool_raw[];
+    __shared__ __align__(16) double s_tab[16];
+    __shared__ double s_part[kBlock / 32][kMaxRegMeas + 1];
+    if (threadIdx.x < 16) s_tab[threadIdx.x] = __longlong_as_double((long long)c_sincos_tab[threadIdx.x]);
+    __syncthreads();
+
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PoolWarp<MR> &P = reinterpret_cast<PoolWarp<MR> *>(s_pool_raw)[warp];
+    const long long N = p.n_walkers;
+    const long long w_first = p.w_begin + (long long)blockIdx.x * kPoolPerBlock + warp * kPoolPerWarp;
+
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {   // slot 32 k + lane <- walker w_first + 32 k + lane
+        const int slot = 32 * k + lane;
+        const long long w = w_first + slot;
+        const bool live = w < p.w_end;
+        if (live) {
+            P.pos[0][slot] = p.pos[3 * w];
+            P.pos[1][slot] = p.pos[3 * w + 1];
+            P.pos[2][slot] = p.pos[3 * w + 2];
+            P.rng[slot] = reinterpret_cast<const ulonglong2 *>(p.rng)[w];
+#pragma unroll
+            for (int m = 0; m < MR; ++m) P.ph[m][slot] = p.t0 > 0 ? p.phases[(long long)m * N + w] : 0.0;
+        }
+        P.t[slot] = p.t0;
+        P.exc[slot] = 0;
+        P.state[slot] = live && p.t0 < p.t1 ? 0 : 2;
+    }
+    __syncwarp();
+
+    // the step is complete: back to the lab frame, final move, phase update with the post-step position
+    auto complete = [&](int slot, Flight &f) {
+        Vec3 pos;
+        const bool e = end_step<SUB>(pos, f, p);
+        const int t = P.t[slot];
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            const double *g = p.grad + ((long long)m * p.n_t + t) * 3;
+            const double gx = __ldg(g), gy = __ldg(g + 1), gz = __ldg(g + 2);
+            P.ph[m][slot] = fma_(p.gamma_dt, fma_(gz, pos.z, fma_(gx, pos.x, mul_(gy, pos.y))), P.ph[m][slot]);
+        }
+        P.pos[0][slot] = pos.x;
+        P.pos[1][slot] = pos.y;
+        P.pos[2][slot] = pos.z;
+        if (e) P.exc[slot] = 1;
+        P.t[slot] = t + 1;
+        P.state[slot] = t + 1 < p.t1 ? 0 : 2;
+    };
+    auto park = [&](int slot, const Flight &f) {   // leave the step in flight in the slot
+        P.pos[0][slot] = f.r0.x;
+        P.pos[1][slot] = f.r0.y;
+        P.pos[2][slot] = f.r0.z;
+        P.dir[0][slot] = f.s.x;
+        P.dir[1][slot] = f.s.y;
+        P.dir[2][slot] = f.s.z;
+        P.step_l[slot] = f.step_l;
+        P.d[slot] = f.d;
+        P.iter[slot] = f.iter;
+    };
+
+    int n_queue = 0, turn = 0;   // warp-uniform
+    for (;;) {
+        const int c0 = lane + 32 * turn, c1 = c0 ^ 32;
+        const int mine = P.state[c0] == 0 ? c0 : (P.state[c1] == 0 ? c1 : -1);
+        const unsigned m_run = __ballot_sync(full, mine >= 0);
+        if (n_queue >= kPoolFlush || (m_run == 0 && n_queue > 0)) {
+            // bounce pass: the first (up to) 32 queued walkers, one per lane
+            const int cnt = min(n_queue, 32);
+            const bool work = lane < cnt;
+            const int slot = work ? P.queue[lane] : 0;
+            const int moved_up = lane + 32 < n_queue ? P.queue[lane + 32] : 0;   // entries beyond the first 32
+            bool again = false;
+            if (work) {
+                Flight f;
+                f.r0 = Vec3{P.pos[0][slot], P.pos[1][slot], P.pos[2][slot]};
+                f.s = Vec3{P.dir[0][slot], P.dir[1][slot], P.dir[2][slot]};
+                f.step_l = P.step_l[slot];
+                f.d = P.d[slot];
+                f.iter = P.iter[slot];
+                bounce<SUB>(f, p);
+                again = probe<SUB>(f, p);
+                if (again) park(slot, f);
+                else complete(slot, f);
+            }
+            __syncwarp();
+            const unsigned m_again = __ballot_sync(full, again);
+            const int kept = __popc(m_again);
+            if (again) P.queue[__popc(m_again & ((1u << lane) - 1u))] = (unsigned char)slot;
+            if (lane + 32 < n_queue) P.queue[kept + lane] = (unsigned char)moved_up;
+            n_queue = kept + max(n_queue - 32, 0);
+            __syncwarp();
+        } else if (m_run == 0) {
+            break;
+        } else {
+            // step pass: a fresh time step for one runnable walker per lane
+            bool hit = false;
+            if (mine >= 0) {
+                Vec3 pos = {P.pos[0][mine], P.pos[1][mine], P.pos[2][mine]};
+                const ulonglong2 st = P.rng[mine];
+                Rng rng = {st.x, st.y};
+                Flight f;
+                f.d = 0.0;
+                begin_step<SUB>(pos, rng, p, s_tab, f);
+                P.rng[mine] = make_ulonglong2(rng.s0, rng.s1);
+                hit = probe<SUB>(f, p);
+                if (hit) {
+                    park(mine, f);
+                    P.state[mine] = 1;
+                } else {
+                    complete(mine, f);
+                }
+            }
+            const unsigned m_hit = __ballot_sync(full, hit);
+            if (hit) P.queue[n_queue + __popc(m_hit & ((1u << lane) - 1u))] = (unsigned char)mine;
+            n_queue += __popc(m_hit);
+            turn ^= 1;
+            __syncwarp();
+        }
+    }
+
+    // state back to global memory; per-half-block partial sums of cos(phase) over unflagged walkers,
+    // laid out like block_signal's (a slot per 128 walkers)
+    double sum[MR + 1];
+#pragma unroll
+    for (int m = 0; m <= MR; ++m) sum[m] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int slot = 32 * k + lane;
+        const long long w = w_first + slot;
+        if (w < p.w_end) {
+            p.pos[3 * w] = P.pos[0][slot];
+            p.pos[3 * w + 1] = P.pos[1][slot];
+            p.pos[3 * w + 2] = P.pos[2][slot];
+            reinterpret_cast<ulonglong2 *>(p.rng)[w] = P.rng[slot];
+            bool exc = P.exc[slot] != 0;
+            if (exc) p.iter_exc[w] = 1;
+            else exc = p.iter_exc[w] != 0;
+#pragma unroll
+            for (int m = 0; m < MR; ++m) {
+                const double ph = P.ph[m][slot];
+                p.phases[(long long)m * N + w] = ph;
+                if (p.finalize && !exc) sum[m] += cos(ph);
+            }
+            if (!exc) sum[MR] += 1.0;
+        }
+    }
+    if (p.finalize) {
+#pragma unroll
+        for (int m = 0; m <= MR; ++m) {
+            const double v = warp_sum(sum[m]);
+            if (lane == 0) s_part[warp][m] = v;
+        }
+        __syncthreads();
+        // warps 0-1 hold the block's first 128 walkers, warps 2-3 the second 128
+        if (threadIdx.x < 2 * (MR + 1)) {
+            const int half = threadIdx.x / (MR + 1), m = threadIdx.x % (MR + 1);
+            const long long first = p.w_begin + (long long)blockIdx.x * kPoolPerBlock + half * kBlock;
+            if (first < p.w_end)
+                p.partials[(long long)m * p.n_blocks_total + (int)(first / kBlock)] = s_part[2 * half][m] + s_part[2 * half + 1][m];
+        }
     }
 }
 
