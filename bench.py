@@ -127,7 +127,11 @@ def cpu_baseline(sub, g, dt, seconds_target=15.0, threads=None):
 # FP64 instructions per unit of the reference's algorithm (read off its SASS)
 W_STEP, W_PHASE, W_REFL, W_TRI = 120, 4, 75, 50
 W_CHECK = {"sphere": 25, "cylinder": 30, "ellipsoid": 75}
-L2_PEAK_BYTES_PER_CLK = 6300.0  # LTS throughput cap, /opt/skills/guides/B300_MICROARCH.md "L2 cache"
+L2_PEAK_BYTES_PER_CLK = 6300.0  # LTS throughput cap, /opt/skills/guides/B300_MICROARCH.md "L2 cache" (a document constant)
+# L2 -> SM traffic the mesh walk ACTUALLY causes: lts__t_sectors.sum x 32 B per walker-step of one ncu --set full
+# capture of walk_kernel<mesh,1> on the config-4 mesh (profiles/r02_f_walk_mesh_config4_ncu.md: 5.747e9 sectors for
+# 5e8 walker-steps; the config-5 mesh: 536 B, profiles/r02_f_walk_mesh_config5_ncu.md)
+NCU_MESH_L2_BYTES_PER_WALKER_STEP = 368.0
 
 
 def algorithmic_work(sub, g, dt, n_sample=2048, pos=None):
@@ -244,7 +248,13 @@ def secondary_workloads(device, fp64_peak, sm_mhz):
             entry["algorithmic_bytes_per_walker_step"] = nbytes
             entry["l2"] = {"achieved_gbs": nbytes * rate / 1e9, "peak_gbs": l2_peak / 1e9,
                            "frac": nbytes * rate / l2_peak,
-                           "peak_source": "6300 B/clk LTS cap (B300_MICROARCH.md) x SM clock"}
+                           "frac_is": "ALGORITHMIC bytes of the reference's search (72 B per ray test it makes + 8 B per cell it "
+                                      "visits) x rate / peak: the kernel's filters avoid most of those tests, so this is work "
+                                      "credited, not hardware utilisation -- hw_frac is",
+                           "hw_bytes_per_walker_step_ncu": NCU_MESH_L2_BYTES_PER_WALKER_STEP,
+                           "hw_frac": NCU_MESH_L2_BYTES_PER_WALKER_STEP * rate / l2_peak,
+                           "peak_source": "DOCUMENT CONSTANT, not measured: 6300 B/clk LTS cap (B300_MICROARCH.md) x the SM clock "
+                                          "sampled during the run"}
         out.append(entry)
     return out
 

@@ -835,30 +835,9 @@ constexpr size_t many_meas_smem()
                                         (dsb::kBlock / 32) * 3 * dsb::ChunkSteps<SUB>::value * 32);
 }
 
-#ifndef DSB_POOL
-#define DSB_POOL 1   // analytic substrates with 1-4 measurements: walker-pool kernel (64 walkers per warp in shared memory)
-#endif
-
-template <int SUB, int MR>
-void launch_pool(const dsb::KParams &kp, cudaStream_t st)
-{
-    constexpr size_t smem = sizeof(dsb::PoolWarp<MR>) * (dsb::kBlock / 32);
-    const int grid = (int)((kp.w_end - kp.w_begin + dsb::kPoolPerBlock - 1) / dsb::kPoolPerBlock);
-    dsb::walk_pool_kernel<SUB, MR><<<grid, dsb::kBlock, smem, st>>>(kp);
-}
-
 template <int SUB, int MAXC>
 void launch_walk_cells(const dsb::KParams &kp, int grid, cudaStream_t st)
 {
-    if constexpr (DSB_POOL && SUB >= 1 && SUB <= 3) {
-        switch (kp.n_meas <= dsb::kMaxRegMeas ? kp.n_meas : 0) {
-        case 1: launch_pool<SUB, 1>(kp, st); return;
-        case 2: launch_pool<SUB, 2>(kp, st); return;
-        case 3: launch_pool<SUB, 3>(kp, st); return;
-        case 4: launch_pool<SUB, 4>(kp, st); return;
-        default: break;
-        }
-    }
     switch (kp.n_meas <= dsb::kMaxRegMeas ? kp.n_meas : 0) {
     case 1: dsb::walk_kernel<SUB, 1, MAXC><<<grid, dsb::kBlock, 0, st>>>(kp); break;
     case 2: dsb::walk_kernel<SUB, 2, MAXC><<<grid, dsb::kBlock, 0, st>>>(kp); break;

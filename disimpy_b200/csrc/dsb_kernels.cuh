@@ -827,6 +827,15 @@ __device__ __forceinline__ bool time_step(Vec3 &pos, Rng &rng, const KParams &p,
     else return walker_step<SUB>(pos, rng, p, tab, live);
 }
 
+// Round 2 measured three designs that give a warp 64 walkers for its 32 lanes so that colliding
+// walkers can be bounced in full batches while the lanes go on with other walkers (walker state in
+// shared memory every step; state in registers and swapped on collision; two walkers per lane in
+// registers): all bit-exact, all slower than this kernel for the sphere and the cylinder (4.4e10-4.9e10
+// against 5.2e10 walker-steps/s; the ellipsoid gained 7 % with one of them, with one measurement only):
+// once the lanes of a warp are at different time steps, the gradient sample, the loop counter and the
+// branches stop being warp-uniform, and that costs more than the ~140 instructions per warp-step the
+// batched reflection saves (profiles/r02_a_kbench.txt, r02_g/h/i_kbench_pool_*.txt).
+//
 // Parked walkers per warp that trigger a bounce pass (1: collisions are handled inline, step by
 // step).  Measured on a B200 (tools/kbench.py, 1e6 walkers): batching pays when the bounce is
 // expensive (ellipsoid: +9 % at 6), not for the sphere and the cylinder (-3 % at 4), where the
@@ -1157,213 +1166,6 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
         p.pos[3 * w + 1] = pos.y;
         p.pos[3 * w + 2] = pos.z;
         reinterpret_cast<ulonglong2 *>(p.rng)[w] = make_ulonglong2(rng.s0, rng.s1);
-    }
-}
-
-// ---------------------------------------------------------------- analytic substrates: walker pool
-
-// Collisions with the wall are rare per walker and step (1-5 %) but not per warp: with one walker
-// per lane the reflection code -- two normalisations, a second distance check, ~340 instructions --
-// runs in 40-75 % of the warp's steps for one or two lanes (round-1 profile: 32 % of the sphere
-// kernel's instructions at 8.6 active lanes).  Here a warp owns 64 walkers whose state lives in
-// shared memory.  A step pass advances one runnable walker per lane (lane l serves walkers l and
-// l + 32, in turn); a walker that hits the wall leaves its step in flight in its slot and joins the
-// warp's queue; once kPoolFlush walkers are queued they are bounced together, one per lane, and
-// either finish their step or stay queued.  Lanes are busy in both kinds of pass, and every walker
-// executes exactly its own sequence of operations (simulations.py:705-875), so trajectories and
-// phases are those of walk_kernel bit for bit.  The price is the walker state's round trip through
-// shared memory every step (~25 instructions) against ~140 saved.
-#ifndef DSB_POOL_FLUSH
-#define DSB_POOL_FLUSH 16
-#endif
-#ifndef DSB_POOL_MIN_BLOCKS
-#define DSB_POOL_MIN_BLOCKS 6
-#endif
-constexpr int kPoolFlush = DSB_POOL_FLUSH;       // queued walkers that trigger a bounce pass
-constexpr int kPoolPerWarp = 64;                 // walkers per warp
-constexpr int kPoolPerBlock = kBlock / 32 * kPoolPerWarp;
-
-// one warp's walkers, structure of arrays (index = slot 0..63)
-template <int MR>
-struct PoolWarp {
-    double pos[3][kPoolPerWarp];   // position between steps; the substrate-frame position r0 of a step in flight
-    double dir[3][kPoolPerWarp];   // unit step of a step in flight
-    double step_l[kPoolPerWarp];   // its remaining length
-    double d[kPoolPerWarp];        // distance to the wall found by its last probe
-    double ph[MR][kPoolPerWarp];
-    ulonglong2 rng[kPoolPerWarp];
-    int t[kPoolPerWarp];           // next time step of the walker
-    int iter[kPoolPerWarp];        // intersection checks made in the step in flight
-    unsigned char state[kPoolPerWarp];   // 0 runnable, 1 step in flight (queued), 2 done (or no walker)
-    unsigned char exc[kPoolPerWarp];
-    unsigned char queue[kPoolPerWarp + 32];
-};
-
-template <int SUB, int MR>
-__global__ void __launch_bounds__(kBlock, DSB_POOL_MIN_BLOCKS) walk_pool_kernel(const __grid_constant__ KParams p)
-{
-    static_assert(SUB >= 1 && SUB <= 3 && MR >= 1 && MR <= kMaxRegMeas, "analytic substrates, phases per walker");
-    extern __shared__ __align__(16) unsigned char s_pool_raw[];
-    __shared__ __align__(16) double s_tab[16];
-    __shared__ double s_part[kBlock / 32][kMaxRegMeas + 1];
-    if (threadIdx.x < 16) s_tab[threadIdx.x] = __longlong_as_double((long long)c_sincos_tab[threadIdx.x]);
-    __syncthreads();
-
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PoolWarp<MR> &P = reinterpret_cast<PoolWarp<MR> *>(s_pool_raw)[warp];
-    const long long N = p.n_walkers;
-    const long long w_first = p.w_begin + (long long)blockIdx.x * kPoolPerBlock + warp * kPoolPerWarp;
-
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {   // slot 32 k + lane <- walker w_first + 32 k + lane
-        const int slot = 32 * k + lane;
-        const long long w = w_first + slot;
-        const bool live = w < p.w_end;
-        if (live) {
-            P.pos[0][slot] = p.pos[3 * w];
-            P.pos[1][slot] = p.pos[3 * w + 1];
-            P.pos[2][slot] = p.pos[3 * w + 2];
-            P.rng[slot] = reinterpret_cast<const ulonglong2 *>(p.rng)[w];
-#pragma unroll
-            for (int m = 0; m < MR; ++m) P.ph[m][slot] = p.t0 > 0 ? p.phases[(long long)m * N + w] : 0.0;
-        }
-        P.t[slot] = p.t0;
-        P.exc[slot] = 0;
-        P.state[slot] = live && p.t0 < p.t1 ? 0 : 2;
-    }
-    __syncwarp();
-
-    // the step is complete: back to the lab frame, final move, phase update with the post-step position
-    auto complete = [&](int slot, Flight &f) {
-        Vec3 pos;
-        const bool e = end_step<SUB>(pos, f, p);
-        const int t = P.t[slot];
-#pragma unroll
-        for (int m = 0; m < MR; ++m) {
-            const double *g = p.grad + ((long long)m * p.n_t + t) * 3;
-            const double gx = __ldg(g), gy = __ldg(g + 1), gz = __ldg(g + 2);
-            P.ph[m][slot] = fma_(p.gamma_dt, fma_(gz, pos.z, fma_(gx, pos.x, mul_(gy, pos.y))), P.ph[m][slot]);
-        }
-        P.pos[0][slot] = pos.x;
-        P.pos[1][slot] = pos.y;
-        P.pos[2][slot] = pos.z;
-        if (e) P.exc[slot] = 1;
-        P.t[slot] = t + 1;
-        P.state[slot] = t + 1 < p.t1 ? 0 : 2;
-    };
-    auto park = [&](int slot, const Flight &f) {   // leave the step in flight in the slot
-        P.pos[0][slot] = f.r0.x;
-        P.pos[1][slot] = f.r0.y;
-        P.pos[2][slot] = f.r0.z;
-        P.dir[0][slot] = f.s.x;
-        P.dir[1][slot] = f.s.y;
-        P.dir[2][slot] = f.s.z;
-        P.step_l[slot] = f.step_l;
-        P.d[slot] = f.d;
-        P.iter[slot] = f.iter;
-    };
-
-    int n_queue = 0, turn = 0;   // warp-uniform
-    for (;;) {
-        const int c0 = lane + 32 * turn, c1 = c0 ^ 32;
-        const int mine = P.state[c0] == 0 ? c0 : (P.state[c1] == 0 ? c1 : -1);
-        const unsigned m_run = __ballot_sync(full, mine >= 0);
-        if (n_queue >= kPoolFlush || (m_run == 0 && n_queue > 0)) {
-            // bounce pass: the first (up to) 32 queued walkers, one per lane
-            const int cnt = min(n_queue, 32);
-            const bool work = lane < cnt;
-            const int slot = work ? P.queue[lane] : 0;
-            const int moved_up = lane + 32 < n_queue ? P.queue[lane + 32] : 0;   // entries beyond the first 32
-            bool again = false;
-            if (work) {
-                Flight f;
-                f.r0 = Vec3{P.pos[0][slot], P.pos[1][slot], P.pos[2][slot]};
-                f.s = Vec3{P.dir[0][slot], P.dir[1][slot], P.dir[2][slot]};
-                f.step_l = P.step_l[slot];
-                f.d = P.d[slot];
-                f.iter = P.iter[slot];
-                bounce<SUB>(f, p);
-                again = probe<SUB>(f, p);
-                if (again) park(slot, f);
-                else complete(slot, f);
-            }
-            __syncwarp();
-            const unsigned m_again = __ballot_sync(full, again);
-            const int kept = __popc(m_again);
-            if (again) P.queue[__popc(m_again & ((1u << lane) - 1u))] = (unsigned char)slot;
-            if (lane + 32 < n_queue) P.queue[kept + lane] = (unsigned char)moved_up;
-            n_queue = kept + max(n_queue - 32, 0);
-            __syncwarp();
-        } else if (m_run == 0) {
-            break;
-        } else {
-            // step pass: a fresh time step for one runnable walker per lane
-            bool hit = false;
-            if (mine >= 0) {
-                Vec3 pos = {P.pos[0][mine], P.pos[1][mine], P.pos[2][mine]};
-                const ulonglong2 st = P.rng[mine];
-                Rng rng = {st.x, st.y};
-                Flight f;
-                f.d = 0.0;
-                begin_step<SUB>(pos, rng, p, s_tab, f);
-                P.rng[mine] = make_ulonglong2(rng.s0, rng.s1);
-                hit = probe<SUB>(f, p);
-                if (hit) {
-                    park(mine, f);
-                    P.state[mine] = 1;
-                } else {
-                    complete(mine, f);
-                }
-            }
-            const unsigned m_hit = __ballot_sync(full, hit);
-            if (hit) P.queue[n_queue + __popc(m_hit & ((1u << lane) - 1u))] = (unsigned char)mine;
-            n_queue += __popc(m_hit);
-            turn ^= 1;
-            __syncwarp();
-        }
-    }
-
-    // state back to global memory; per-half-block partial sums of cos(phase) over unflagged walkers,
-    // laid out like block_signal's (a slot per 128 walkers)
-    double sum[MR + 1];
-#pragma unroll
-    for (int m = 0; m <= MR; ++m) sum[m] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int slot = 32 * k + lane;
-        const long long w = w_first + slot;
-        if (w < p.w_end) {
-            p.pos[3 * w] = P.pos[0][slot];
-            p.pos[3 * w + 1] = P.pos[1][slot];
-            p.pos[3 * w + 2] = P.pos[2][slot];
-            reinterpret_cast<ulonglong2 *>(p.rng)[w] = P.rng[slot];
-            bool exc = P.exc[slot] != 0;
-            if (exc) p.iter_exc[w] = 1;
-            else exc = p.iter_exc[w] != 0;
-#pragma unroll
-            for (int m = 0; m < MR; ++m) {
-                const double ph = P.ph[m][slot];
-                p.phases[(long long)m * N + w] = ph;
-                if (p.finalize && !exc) sum[m] += cos(ph);
-            }
-            if (!exc) sum[MR] += 1.0;
-        }
-    }
-    if (p.finalize) {
-#pragma unroll
-        for (int m = 0; m <= MR; ++m) {
-            const double v = warp_sum(sum[m]);
-            if (lane == 0) s_part[warp][m] = v;
-        }
-        __syncthreads();
-        // warps 0-1 hold the block's first 128 walkers, warps 2-3 the second 128
-        if (threadIdx.x < 2 * (MR + 1)) {
-            const int half = threadIdx.x / (MR + 1), m = threadIdx.x % (MR + 1);
-            const long long first = p.w_begin + (long long)blockIdx.x * kPoolPerBlock + half * kBlock;
-            if (first < p.w_end)
-                p.partials[(long long)m * p.n_blocks_total + (int)(first / kBlock)] = s_part[2 * half][m] + s_part[2 * half + 1][m];
-        }
     }
 }
 

@@ -32,6 +32,8 @@ def make(case):
         sub, n_meas, n_t = substrates.sphere(10e-6), 8, 1000
     elif case == "cylinder":
         sub = substrates.cylinder(5e-6, np.array([0.0, 0.0, 1.0]))
+    elif case == "cylinder_t1e4":
+        sub, n_t = substrates.cylinder(5e-6, np.array([0.0, 0.0, 1.0])), 10000
     elif case == "ellipsoid":
         sub = substrates.ellipsoid(np.array([10e-6, 5e-6, 2.5e-6]),
                                    utils.vec2vec_rotmat(np.array([1.0, 0, 0]), np.array([1.0, 1.0, 1.0])))
