@@ -1486,6 +1486,33 @@ int dsb_measure_fp64_peak(int32_t device, double *dfma_per_second)
     return DSB_OK;
 }
 
+int dsb_selftest_sqrt(int32_t device, uint64_t seed, int32_t exp_lo, int32_t exp_hi, int64_t n, int64_t *n_mismatch,
+                      double *first_mismatch)
+{
+    if (!n_mismatch || exp_lo < -969 || exp_hi > 1022 || exp_hi < exp_lo || n <= 0) return fail(DSB_EINVAL, "bad arguments");
+    DSB_CUDA(cudaSetDevice(device));
+    unsigned long long *d_bad = nullptr;
+    double *d_first = nullptr;
+    DSB_CUDA(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+    DSB_CUDA(cudaMalloc(&d_first, sizeof(double)));
+    DSB_CUDA(cudaMemset(d_bad, 0, sizeof(unsigned long long)));
+    DSB_CUDA(cudaMemset(d_first, 0, sizeof(double)));
+    const int per_thread = 4096, threads = 256;
+    const int64_t blocks = std::max<int64_t>(1, (n + (int64_t)per_thread * threads - 1) / ((int64_t)per_thread * threads));
+    dsb::sqrt_selftest_kernel<<<(unsigned)std::min<int64_t>(blocks, 0x7fffffff), threads>>>(seed, exp_lo, exp_hi, per_thread, d_bad,
+                                                                                           d_first);
+    unsigned long long bad = 0;
+    double first = 0.0;
+    cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&first, d_first, sizeof first, cudaMemcpyDeviceToHost);
+    cudaFree(d_bad);
+    cudaFree(d_first);
+    if (e != cudaSuccess) return fail(DSB_ECUDA, cudaGetErrorString(e));
+    *n_mismatch = (int64_t)bad;
+    if (first_mismatch) *first_mismatch = first;
+    return DSB_OK;
+}
+
 int dsb_protocol_rank(dsb_sim *s) { return s ? s->rank : 0; }
 
 int dsb_protocol_factor(const double *gradient, int64_t n_meas, int64_t n_t, int32_t max_rank, int32_t *rank, double *u,

@@ -11,8 +11,15 @@ namespace dsb {
 #ifndef DSB_BLOCK
 #define DSB_BLOCK 128
 #endif
+// Blocks per SM the register-phase kernels of the free and analytic substrates are compiled for.  Left
+// alone, the step generator's straight-line code (round 2: no branches around square roots and
+// divisions any more) lets ptxas spend 94-120 registers on it; capped at 6 blocks (80 registers; the
+// ellipsoid: 7, 72 registers) it is 2-12 % faster (profiles/r02_j_kbench_sqrt_fast.txt).
 #ifndef DSB_MIN_BLOCKS
-#define DSB_MIN_BLOCKS 1
+#define DSB_MIN_BLOCKS 6
+#endif
+#ifndef DSB_MIN_BLOCKS_ELLIPSOID
+#define DSB_MIN_BLOCKS_ELLIPSOID 7
 #endif
 #ifndef DSB_MR0_MIN_BLOCKS
 #define DSB_MR0_MIN_BLOCKS 4
@@ -91,10 +98,9 @@ struct KParams {
 // ---------------------------------------------------------------- one time step, per substrate
 
 // simulations.py:682-702
-__device__ __forceinline__ bool free_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab, const bool live)
+__device__ __forceinline__ bool free_step(Vec3 &pos, const Vec3 &s, const KParams &p, const bool live)
 {
     if (!live) return false;
-    Vec3 s = random_step(rng, tab);
     pos.x = fma_(s.x, p.step_l, pos.x);
     pos.y = fma_(s.y, p.step_l, pos.y);
     pos.z = fma_(s.z, p.step_l, pos.z);
@@ -115,10 +121,9 @@ struct Flight {      // one time step in progress
 // new random direction; position into the substrate frame (simulations.py:722-728, 778-787,
 // 838-847).  The step is not rotated in, like the reference.
 template <int SUB>
-__device__ __forceinline__ void begin_step(const Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
-                                           Flight &f)
+__device__ __forceinline__ void begin_step(const Vec3 &pos, const Vec3 &unit, const KParams &p, Flight &f)
 {
-    f.s = random_step(rng, tab);
+    f.s = unit;
     if constexpr (SUB == 2 || SUB == 3) f.r0 = matvec3(p.R, pos);
     else f.r0 = pos;
     f.step_l = p.step_l;
@@ -190,13 +195,12 @@ __device__ __forceinline__ bool end_step(Vec3 &pos, Flight &f, const KParams &p)
 
 // simulations.py:705-756 (sphere), :759-816 (cylinder), :819-875 (ellipsoid)
 template <int SUB>
-__device__ __forceinline__ bool walker_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab,
-                                            const bool live)
+__device__ __forceinline__ bool walker_step(Vec3 &pos, const Vec3 &unit, const KParams &p, const bool live)
 {
     static_assert(SUB >= 1 && SUB <= 3, "analytic substrates only");
     if (!live) return false;
     Flight f;
-    begin_step<SUB>(pos, rng, p, tab, f);
+    begin_step<SUB>(pos, unit, p, f);
     while (probe<SUB>(f, p)) bounce<SUB>(f, p);
     return end_step<SUB>(pos, f, p);
 }
@@ -820,11 +824,11 @@ __device__ __forceinline__ void block_signal(const KParams &p, bool valid, Phase
 // ---------------------------------------------------------------- the walk kernel
 
 template <int SUB>
-__device__ __forceinline__ bool time_step(Vec3 &pos, Rng &rng, const KParams &p, const double *tab, const bool live)
+__device__ __forceinline__ bool time_step(Vec3 &pos, const Vec3 &unit, const KParams &p, const bool live)
 {
     static_assert(SUB != 4, "the mesh walk has its own time loop (mesh_walk)");
-    if constexpr (SUB == 0) return free_step(pos, rng, p, tab, live);
-    else return walker_step<SUB>(pos, rng, p, tab, live);
+    if constexpr (SUB == 0) return free_step(pos, unit, p, live);
+    else return walker_step<SUB>(pos, unit, p, live);
 }
 
 // Round 2 measured three designs that give a warp 64 walkers for its 32 lanes so that colliding
@@ -867,7 +871,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 // are buffered in registers, then each measurement's phase makes one round trip through its
 // (coalesced, L2-resident) row of `phases` per chunk instead of one per step.
 template <int SUB, int MR, int MAXC = kMaxCells>
-__global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR == 0 ? DSB_MR0_MIN_BLOCKS : DSB_MIN_BLOCKS)) walk_kernel(const __grid_constant__ KParams p)
+__global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR == 0 ? DSB_MR0_MIN_BLOCKS : (SUB == 3 ? DSB_MIN_BLOCKS_ELLIPSOID : DSB_MIN_BLOCKS))) walk_kernel(const __grid_constant__ KParams p)
 {
     __shared__ __align__(16) double s_tab[16];
     if (threadIdx.x < 16) s_tab[threadIdx.x] = __longlong_as_double((long long)c_sincos_tab[threadIdx.x]);
@@ -937,7 +941,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
                     if (parked) bounce<SUB>(f, p);
                 } else {
                     moved = fresh;
-                    if (fresh) begin_step<SUB>(pos, rng, p, s_tab, f);
+                    if (fresh) begin_step<SUB>(pos, random_step(rng, s_tab), p, f);
                 }
                 if (moved) {
                     parked = probe<SUB>(f, p);
@@ -958,7 +962,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
         } else {
             // the time loop is uniform over the block
             for (int t = p.t0; t < p.t1; ++t) {
-                exc |= time_step<SUB>(pos, rng, p, s_tab, active);
+                exc |= time_step<SUB>(pos, random_step(rng, s_tab), p, active);
                 accumulate(t);
             }
         }
@@ -1052,7 +1056,7 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
             } else {
 #pragma unroll 1
                 for (int k = 0; k < cnt; ++k) {
-                    exc |= time_step<SUB>(pos, rng, p, s_tab, active);
+                    exc |= time_step<SUB>(pos, random_step(rng, s_tab), p, active);
                     x_at(3 * k, lane) = pos.x;
                     x_at(3 * k + 1, lane) = pos.y;
                     x_at(3 * k + 2, lane) = pos.z;
@@ -1253,6 +1257,33 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 #pragma unroll
     for (int k = 0; k < kPeakChains; ++k) sum += a[k];
     out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+// ---------------------------------------------------------------- self-test of sqrt_fast
+
+// sqrt_fast(x) against __dsqrt_rn(x), bit for bit, on pseudo-random arguments: thread i tests `per_thread`
+// values whose exponent is uniform in [e_lo, e_hi] and whose mantissa bits come from a 64-bit mixer.
+__global__ void __launch_bounds__(256) sqrt_selftest_kernel(unsigned long long seed, int e_lo, int e_hi, int per_thread,
+                                                            unsigned long long *n_bad, double *first_bad)
+{
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1);
+    int bad = 0;
+    for (int k = 0; k < per_thread; ++k) {
+        z += 0x9E3779B97F4A7C15ULL;
+        unsigned long long v = z;
+        v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        v = (v ^ (v >> 27)) * 0x94D049BB133111EBULL;
+        v ^= v >> 31;
+        const unsigned long long mant = v & 0x000FFFFFFFFFFFFFULL;
+        const int e = e_lo + (int)((v >> 52) % (unsigned long long)(e_hi - e_lo + 1));
+        const double x = __longlong_as_double((long long)(((unsigned long long)(e + 1023) << 52) | mant));
+        const double a = sqrt_fast(x), b = __dsqrt_rn(x);
+        if (__double_as_longlong(a) != __double_as_longlong(b)) {
+            if (bad == 0 && atomicAdd(n_bad, 0ull) == 0ull) *first_bad = x;
+            ++bad;
+        }
+    }
+    if (bad) atomicAdd(n_bad, (unsigned long long)bad);
 }
 
 // ---------------------------------------------------------------- RNG state derivation
