@@ -811,6 +811,7 @@ struct dsb_sim {
     unsigned long long *d_rng = nullptr, *d_rng0 = nullptr;
     unsigned char *d_exc = nullptr;
     MeshBuffers mesh;
+    dsb::EllipsoidConsts ell{};   // DSB_ELLIPSOID: semi-axes and what the distance check derives from them
     int rank = 0;            // > 0: low-rank protocol, the walk carries `rank` virtual measurements
     double *d_u = nullptr;   // (n_meas, rank) coefficients of the real measurements
     int64_t t_cur = -1;  // -1: positions not set
@@ -1133,6 +1134,22 @@ static int create_impl(const dsb_params *params, const double *gradient, dsb_sim
             return fail(rc, keep);
         }
     }
+    if (params->substrate == DSB_ELLIPSOID) {
+        // reciprocals of the semi-axes etc., computed on the device with the step kernel's own functions
+        dsb::EllipsoidConsts *d_ell = nullptr;
+        cudaError_t e = cudaMalloc(&d_ell, sizeof(dsb::EllipsoidConsts));
+        if (e == cudaSuccess) {
+            dsb::ellipsoid_consts_kernel<<<1, 1, 0, s->stream>>>(params->semiaxes[0], params->semiaxes[1], params->semiaxes[2], d_ell);
+            e = cudaMemcpyAsync(&s->ell, d_ell, sizeof(dsb::EllipsoidConsts), cudaMemcpyDeviceToHost, s->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        cudaFree(d_ell);
+        if (e != cudaSuccess) {
+            std::string msg = std::string("ellipsoid constants: ") + cudaGetErrorString(e);
+            dsb_destroy(s), *live = nullptr;
+            return fail(DSB_ECUDA, msg);
+        }
+    }
     s->prm.mesh = dsb_mesh{};  // host pointers are not kept
     rc = launch_rng_init(params->device, params->seed, (uint64_t)params->walker_offset, N,
                          reinterpret_cast<ulonglong2 *>(s->d_rng0), s->stream);
@@ -1216,7 +1233,7 @@ static int launch_walk_range(dsb_sim *s, cudaStream_t st, int64_t w0, int64_t w1
     kp.radius = P.radius;
     memcpy(kp.R, P.R, sizeof kp.R);
     memcpy(kp.Rinv, P.R_inv, sizeof kp.Rinv);
-    memcpy(kp.ax, P.semiaxes, sizeof kp.ax);
+    kp.ell = s->ell;
     kp.grad = s->d_grad;
     kp.grad_chunked = s->d_grad_chunked;
     kp.pos = s->d_pos;

@@ -84,7 +84,8 @@ struct KParams {
     int finalize;  // t1 == n_t: also emit per-block sum(cos phase) partials
     int max_iter;  // clamped to INT_MAX by the host
     double step_l, gamma_dt, eps, radius;
-    double R[9], Rinv[9], ax[3];
+    double R[9], Rinv[9];
+    EllipsoidConsts ell;
     const double *grad;         // (n_meas, n_t, 3)
     const double *grad_chunked; // (ceil(n_t / chunk), n_meas, grad_row_len(chunk)): gamma dt g, zero padded
     double *pos;                // (n_walkers, 3)
@@ -140,7 +141,7 @@ __device__ __forceinline__ bool probe(Flight &f, const KParams &p)
     ++f.iter;
     if constexpr (SUB == 1) f.d = line_sphere(f.r0, f.s, p.radius);
     else if constexpr (SUB == 2) f.d = line_circle(f.r0, f.s, p.radius);
-    else f.d = line_ellipsoid(f.r0, f.s, p.ax);
+    else f.d = line_ellipsoid(f.r0, f.s, p.ell);
     return f.d > 0 && f.d < f.step_l;
 }
 
@@ -168,9 +169,15 @@ __device__ __forceinline__ void bounce(Flight &f, const KParams &p)
             n.z = div_(-X2, len);
         }
     } else {
-        n.x = div_(-fma_(f.d, f.s.x, f.r0.x), mul_(p.ax[0], p.ax[0]));
-        n.y = div_(-fma_(f.d, f.s.y, f.r0.y), mul_(p.ax[1], p.ax[1]));
-        n.z = div_(-fma_(f.d, f.s.z, f.r0.z), mul_(p.ax[2], p.ax[2]));
+        const double nx = -fma_(f.d, f.s.x, f.r0.x), ny = -fma_(f.d, f.s.y, f.r0.y), nz = -fma_(f.d, f.s.z, f.r0.z);
+        bool ok = div_fast(nx, p.ell.axsq[0], p.ell.axsq_rc[0], n.x);
+        ok &= div_fast(ny, p.ell.axsq[1], p.ell.axsq_rc[1], n.y);
+        ok &= div_fast(nz, p.ell.axsq[2], p.ell.axsq_rc[2], n.z);
+        if (!ok) {
+            n.x = div_(nx, p.ell.axsq[0]);
+            n.y = div_(ny, p.ell.axsq[1]);
+            n.z = div_(nz, p.ell.axsq[2]);
+        }
         n = normalize3(n);
     }
     reflect(f.r0, f.s, f.d, n, p.eps);
@@ -1257,6 +1264,20 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 #pragma unroll
     for (int k = 0; k < kPeakChains; ++k) sum += a[k];
     out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+// ---------------------------------------------------------------- ellipsoid constants
+
+__global__ void ellipsoid_consts_kernel(double a0, double a1, double a2, EllipsoidConsts *out)
+{
+    const double ax[3] = {a0, a1, a2};
+    for (int k = 0; k < 3; ++k) {
+        out->ax[k] = ax[k];
+        out->ax_rc[k] = rcp_refined(ax[k]);
+        out->axsq[k] = mul_(ax[k], ax[k]);
+        out->ax_isq[k] = rcp_(out->axsq[k]);
+        out->axsq_rc[k] = rcp_refined(out->axsq[k]);
+    }
 }
 
 // ---------------------------------------------------------------- self-test of sqrt_fast
