@@ -14,6 +14,11 @@ Prints ONE JSON line.  `value` = walker-steps/s with inputs resident in HBM, tim
 events on the library's stream around the K timed steps (max over ranks); `e2e` = the same
 through the public disimpy_b200.simulations.simulation() call with host buffers (initial
 positions sampled on the host, H2D, kernels, D2H of the signal inside the timed region).
+Beside the contract's keys: `mesh` = BASELINE configs 4 and 5 (the mesh half of the metric)
+through simulation() on EVERY rank of the run; at N = 1 also `other_workloads` (kernel rates and
+roofline fractions of the other configurations), `e2e_default_verbose_call` (quiet=False) and
+`baselines` (the unmodified reference timed in the same run: its Numba-CUDA kernels on this GPU
+and its NUMBA_ENABLE_CUDASIM path on the host, with the ratios).
 `--impl reference` times the CPU restatement of the reference's algorithm (oracle/, all host
 threads) on a bounded sample of the same workload.
 """
@@ -48,8 +53,8 @@ FP64_PER_WALKER_STEP = 120 + 25 + 4 * 1
 # (32), phase out (8), iter_exc (1)
 HBM_BYTES_PER_WALKER = 48 + 32 + 8 + 1
 # dram__bytes_read.sum + dram__bytes_write.sum of one walk_kernel<sphere,1> launch over 1e6 walkers
-# (profiles/r01_k_walk_sphere_ncu.md; independent of the number of steps in the launch)
-NCU_DRAM_BYTES_PER_LAUNCH = 41.05e6 + 1.27e6
+# (profiles/r02_j_walk_sphere_ncu.md; independent of the number of steps in the launch)
+NCU_DRAM_BYTES_PER_LAUNCH = 41.07e6 + 0.66e6
 
 
 def workload():
@@ -370,7 +375,20 @@ def run_reference(args, rank):
                          "sample": "%d walkers x %d steps per step" % (n, N_T)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "what_this_is": "the repo's C PORT of the reference's algorithm (oracle/, test infrastructure) on all host "
+                        "threads -- far faster than anything the reference ships for CPUs: its own CPU path "
+                        "(NUMBA_ENABLE_CUDASIM=1, Python threads under the GIL) runs at ~4e2 walker-steps/s "
+                        "(`cudasim` below, when oracle/_ref is present), and its Numba-CUDA path on the GPU is timed "
+                        "in the b200 arm's `baselines`",
     }
+    if os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "disimpy")):
+        try:
+            res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_reference_cudasim.py"), "128", "50", "--json"],
+                                 capture_output=True, text=True, timeout=300)
+            out = [l for l in res.stdout.splitlines() if l.startswith("{")]
+            line["cudasim"] = json.loads(out[-1]) if out else {"unavailable": (res.stderr or res.stdout)[-200:]}
+        except Exception as e:
+            line["cudasim"] = {"unavailable": repr(e)}
     print(json.dumps(line), flush=True)
 
 

@@ -340,10 +340,10 @@ struct HostBuf {
 // fn(begin, end) over [0, n) in contiguous pieces on a few host threads (the re-layout loops below
 // are independent per element; a 1e6-triangle mesh has ~1e7 of them)
 template <typename Fn>
-void parallel_ranges(int64_t n, Fn fn)
+void parallel_ranges(int64_t n, Fn fn, int64_t grain = 65536)
 {
     unsigned hw = std::thread::hardware_concurrency();
-    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)(hw ? hw : 1), n / 65536}));
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)(hw ? hw : 1), n / grain}));
     if (n_threads <= 1) {
         fn((int64_t)0, n);
         return;
@@ -504,9 +504,10 @@ int build_search_grid(const dsb_mesh &m, const HostBuf<int2> &cells, const HostB
     parallel_ranges(n_fine, [&](int64_t a, int64_t b) {
         for (int64_t i = a; i < b; ++i) fcells[(size_t)i] = make_int2(0, 0);
     });
+    const int64_t grain = 8192;   // (k^3 x list length box tests per parent cell: worth a thread much earlier than a copy loop)
     parallel_ranges(n_coarse, [&](int64_t c0, int64_t c1) {
         for (int64_t c = c0; c < c1; ++c) for_sub_cells(c, [&](int64_t fi, int) { ++fcells[(size_t)fi].y; });
-    });
+    }, grain);
     int64_t total = 0;
     for (int64_t i = 0; i < n_fine; ++i) {
         const int cnt = fcells[(size_t)i].y;
@@ -519,7 +520,7 @@ int build_search_grid(const dsb_mesh &m, const HostBuf<int2> &cells, const HostB
     parallel_ranges(n_coarse, [&](int64_t c0, int64_t c1) {   // (a sub-cell belongs to one parent: no two threads share a cursor)
         for (int64_t c = c0; c < c1; ++c)
             for_sub_cells(c, [&](int64_t fi, int t) { fentry[(size_t)fcells[(size_t)fi].y++] = box[(size_t)t]; });
-    });
+    }, grain);
     fentry[(size_t)total] = make_uint4(0u, 0u, 0u, 0u);
     DSB_CUDA(cache_malloc(&mb.f_entry, fentry.size() * sizeof(uint4)));
     DSB_CUDA(cache_malloc(&mb.f_cell_rng, fcells.size() * sizeof(int2)));
