@@ -346,7 +346,6 @@ struct MeshScratch {
         double hit[kSurvivorCap];       // distance found for the survivor (inf: none)
     };
     int2 range_pos[kRangeCap];      // number of the range's first entry in the warp's flat numbering; its place in the list
-    int2 cell_tmp[8][32];           // short-step variant: the list ranges of each lane's eight cell slots
     unsigned start_bits[kEntryCap / 32 + 1];    // bit j: a range starts at flat entry j (+ a word of padding)
     unsigned long long survivor[kSurvivorCap];  // triangle (32) | owner lane (8) | image flags (3) << 8
 };
@@ -489,7 +488,6 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
     int off_x[2] = {0, 0}, off_y[2] = {0, 0}, off_z[2] = {0, 0};  // row offsets of the (wrapped) cells per axis
     int wrap_x = 0, wrap_y = 0, wrap_z = 0;                        // the second cell lies in the next image
     int n_cells_warp = 0;
-    unsigned slot_mask = 0u;                                       // short steps: the slots whose lists are not empty
     if constexpr (MAXC == kMaxCellsShortStep) {
         if (fast) {
             int c1 = sx.cell + 1;
@@ -510,11 +508,6 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
             const int ix = c >> 2, iy = (c >> 1) & 1, iz = c & 1;
             if (fast && ix < sx.count && iy < sy.count && iz < sz.count)
                 rng[c] = __ldg(f.cell_rng + off_x[ix] + off_y[iy] + off_z[iz]);
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            sc.cell_tmp[c][lane] = rng[c];
-            slot_mask |= (rng[c].y > rng[c].x ? 1u : 0u) << c;
         }
     } else {
         // general spans: the loops stop at the largest cell count of the warp
@@ -588,22 +581,12 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
             }
         };
         if constexpr (MAXC == kMaxCellsShortStep) {
-            // Only the slots with entries, in slot order: a lane typically has one to three of its eight, so
-            // the warp runs this body as often as its busiest lane has non-empty cells instead of eight times
-            // with a handful of lanes each (round-2 profile: 257 instructions per warp-step at 5 active lanes).
-            for (unsigned m = slot_mask; m != 0u; m &= m - 1u) {
-                const int c = __ffs((int)m) - 1;
-                const int2 r = sc.cell_tmp[c][lane];
-                const int fx = (c >> 2) & wrap_x, fy = ((c >> 1) & 1) & wrap_y, fz = (c & 1) & wrap_z;
-                sc.range_box[k] = make_uint4(((fx ? hx[1] : hx[0]) | ((fy ? hy[1] : hy[0]) << 16)) + kSwarH,
-                                             ((fz ? hz[1] : hz[0]) | ((fx ? lx[1] : lx[0]) << 16)) + kSwarH,
-                                             ((fy ? ly[1] : ly[0]) | ((fz ? lz[1] : lz[0]) << 16)) + kSwarH,
-                                             (unsigned)lane | ((unsigned)(fx | (fy << 1) | (fz << 2)) << 8));
-                sc.range_pos[k] = make_int2(first, r.x);
-                atomicOr(&sc.start_bits[first >> 5], 1u << (first & 31));
-                ++k;
-                first += r.y - r.x;
-            }
+            // (All eight slots, unrolled and predicated, although a lane has entries in one to three of them --
+            // 257 instructions per warp-step at 5 active lanes.  A loop over the lane's non-empty slots only, their
+            // ranges parked in shared memory, was measured: -21 %, profiles/r02_n_kbench_range_loop.txt.)
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                add_range(c, ((c >> 2) & wrap_x) | ((((c >> 1) & 1) & wrap_y) << 1) | (((c & 1) & wrap_z) << 2));
         } else {
             CellWalk cw;
 #pragma unroll
