@@ -449,14 +449,18 @@ def main():
     walk = simulations.Walk(params, g)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     sig_buf = torch.zeros(2, dtype=torch.float64, device="cuda")
+    comm = simulations.library_comm(dist, rank, world) if world > 1 else None
 
     def one_step():
         walk.set_positions_dev(d_pos0.data_ptr())
         walk.run(0, N_T)
+        if world > 1 and comm:
+            sig, n_valid = walk.allreduce_signal(comm)   # the one collective of the path: NCCL all-reduce inside the
+            return sig[0], n_valid                       # library, in place on its result buffer and stream; 16 bytes D2H
         if world > 1:
-            walk.copy_signal_to(sig_buf.data_ptr())   # waits for the walk; (sum cos, valid count) stay on the device
-            dist.all_reduce(sig_buf)                  # the one collective of the path (NCCL)
-            out = sig_buf.cpu().numpy()               # 16 bytes D2H
+            walk.copy_signal_to(sig_buf.data_ptr())   # (fallback through torch.distributed)
+            dist.all_reduce(sig_buf)
+            out = sig_buf.cpu().numpy()
             return out[0], int(round(out[1]))
         sig, n_valid = walk.signal()          # syncs the library's stream, 16 bytes D2H
         return sig[0], n_valid
@@ -600,6 +604,9 @@ def main():
                                    "delta=10ms DELTA=30ms b=1e9 s/m^2 (1 measurement), D=2e-9 m^2/s, "
                                    "seed 123" % (N_WALKERS, N_T),
                        "walkers_total": n_global, "parallelism": "walker shards x%d" % world,
+                       "collective": ("one NCCL all-reduce of 2 doubles per step, issued by the library (dsb_allreduce_signal)"
+                                      if comm else "one NCCL all-reduce of 2 doubles per step through torch.distributed")
+                       if world > 1 else "none (1 GPU)",
                        "l2": "256 MB flush between timed iterations"},
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,

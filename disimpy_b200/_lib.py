@@ -71,6 +71,7 @@ EXPORTS = [
     "dsb_set_rng_states", "dsb_fill_mesh_sim", "dsb_protocol_rank", "dsb_protocol_factor", "dsb_set_rng_part", "dsb_host_sampler_create", "dsb_host_sampler_next", "dsb_host_sampler_destroy",
     "dsb_fill_shard_begin", "dsb_fill_shard_round", "dsb_fill_shard_end",
     "dsb_copy_signal_dev", "dsb_simulate_multi", "dsb_fill_mesh_multi", "dsb_selftest_sqrt",
+    "dsb_nccl_unique_id", "dsb_nccl_init", "dsb_allreduce_signal", "dsb_allreduce_zeros", "dsb_nccl_destroy",
 ]
 
 _lib = None
@@ -147,6 +148,12 @@ def lib():
                                           ctypes.c_uint64, ctypes.c_int64]
         L.dsb_selftest_sqrt.argtypes = [ctypes.c_int32, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                         c_int64_p, c_double_p]
+        L.dsb_nccl_unique_id.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+        L.dsb_nccl_init.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                    ctypes.POINTER(ctypes.c_void_p)]
+        L.dsb_allreduce_signal.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_int64_p]
+        L.dsb_allreduce_zeros.argtypes = [ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, c_int64_p]
+        L.dsb_nccl_destroy.argtypes = [ctypes.c_void_p]
         L.dsb_release_cache.argtypes = []
         L.dsb_device_count.argtypes = [ctypes.POINTER(ctypes.c_int32)]
         L.dsb_triangle_box_overlap.argtypes = [ctypes.c_void_p, ctypes.c_void_p]

@@ -11,12 +11,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <new>
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
 #include <nvtx3/nvToolsExt.h>
 
 namespace {
@@ -375,6 +377,11 @@ struct MeshBuffers {
     int2 *f_cell_rng = nullptr;
     double *f_xs = nullptr, *f_ys = nullptr, *f_zs = nullptr;
     int refine[3] = {1, 1, 1};
+    std::mutex mu;   // the sampler's column lists are built on first use; handles may share one upload
+    MeshBuffers() = default;
+    MeshBuffers(const MeshBuffers &) = delete;
+    MeshBuffers &operator=(const MeshBuffers &) = delete;
+    ~MeshBuffers() { release(); }
     void release()
     {
         cache_free(f_entry);
@@ -393,7 +400,14 @@ struct MeshBuffers {
         cache_free(xs);
         cache_free(ys);
         cache_free(zs);
-        *this = MeshBuffers();
+        f_entry = nullptr, f_cell_rng = nullptr, f_xs = f_ys = f_zs = nullptr;
+        col_start = col_cnt = nullptr, col_entry = nullptr;
+        tri = normal = nullptr, tri_idx = nullptr, entry = nullptr, cell_rng = nullptr, xs = ys = zs = nullptr;
+        columns = dsb::FillColumns{};
+        dev = dsb::MeshDev{};
+        h_cells = HostBuf<int2>();
+        h_tri_idx = HostBuf<int>();
+        h_box = HostBuf<uint4>();
     }
 };
 
@@ -724,6 +738,7 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb, double step_l = 0.0)
 // triangles of its cells, those of the last x cell first.  One pass over the cell lists.
 int build_fill_columns(MeshBuffers &mb)
 {
+    std::lock_guard<std::mutex> lk(mb.mu);
     if (mb.columns.entry) return DSB_OK;
     Range nvtx("dsb: sampler column lists");
     const int64_t n0 = mb.n_sv[0], n1 = mb.n_sv[1], n2 = mb.n_sv[2];
@@ -792,6 +807,102 @@ int build_fill_columns(MeshBuffers &mb)
     return DSB_OK;
 }
 
+// ------------------------------------------------------------- uploaded meshes, kept between handles
+
+// simulation() is usually called many times on one substrate (other protocols, other seeds), and each
+// call hands the library the same mesh arrays again.  Re-laying them out, uploading them and refining
+// the search grid costs 12 ms for the 1e5-triangle mesh of BASELINE config 4 next to a 97 ms walk, 70
+// ms for the 1e6-triangle mesh.  The last uploads are therefore kept per device, found again by a
+// 64-bit fingerprint of every input array (plus sizes and the refinement the step length asks for),
+// and shared by the handles that use them.  DISIMPY_B200_MESH_CACHE=0 turns this off.
+uint64_t fingerprint(const void *data, size_t bytes, uint64_t seed)
+{
+    const size_t n_words = bytes / 8;
+    const uint64_t *w = static_cast<const uint64_t *>(data);
+    const int64_t n_chunks = (int64_t)std::max<size_t>(1, std::min<size_t>(64, n_words / 32768));
+    std::vector<uint64_t> part((size_t)n_chunks, 0);
+    parallel_ranges(n_chunks, [&](int64_t c0, int64_t c1) {
+        for (int64_t c = c0; c < c1; ++c) {
+            uint64_t h0 = seed ^ (uint64_t)c, h1 = ~seed, h2 = seed * 3, h3 = seed + 0x9E3779B97F4A7C15ULL;
+            size_t i = n_words * (size_t)c / (size_t)n_chunks;
+            const size_t end = n_words * (size_t)(c + 1) / (size_t)n_chunks;
+            for (; i + 4 <= end; i += 4) {   // four independent lanes: multiply latency hidden
+                h0 = (h0 ^ w[i]) * 0x9E3779B97F4A7C15ULL;
+                h1 = (h1 ^ w[i + 1]) * 0xC2B2AE3D27D4EB4FULL;
+                h2 = (h2 ^ w[i + 2]) * 0x165667B19E3779F9ULL;
+                h3 = (h3 ^ w[i + 3]) * 0xD6E8FEB86659FD93ULL;
+                h0 ^= h0 >> 29, h1 ^= h1 >> 31, h2 ^= h2 >> 27, h3 ^= h3 >> 30;
+            }
+            for (; i < end; ++i) h0 = (h0 ^ w[i]) * 0x9E3779B97F4A7C15ULL, h0 ^= h0 >> 29;
+            part[(size_t)c] = (h0 * 31 + h1) ^ ((h2 * 17 + h3) << 1);
+        }
+    }, 1);
+    uint64_t h = seed ^ (uint64_t)bytes;
+    for (uint64_t v : part) h = (h ^ v) * 0x9E3779B97F4A7C15ULL, h ^= h >> 32;
+    const unsigned char *tail = static_cast<const unsigned char *>(data) + n_words * 8;
+    for (size_t i = 0; i < bytes % 8; ++i) h = (h ^ tail[i]) * 0x100000001B3ULL;
+    return h;
+}
+
+struct MeshKey {
+    int device = -1;
+    uint64_t hash = 0;
+    int64_t n_faces = 0, n_vertices = 0, n_tri = 0, n_sv[3] = {0, 0, 0};
+    int refine[3] = {1, 1, 1};
+    bool operator==(const MeshKey &o) const
+    {
+        return device == o.device && hash == o.hash && n_faces == o.n_faces && n_vertices == o.n_vertices && n_tri == o.n_tri &&
+               n_sv[0] == o.n_sv[0] && n_sv[1] == o.n_sv[1] && n_sv[2] == o.n_sv[2] && refine[0] == o.refine[0] &&
+               refine[1] == o.refine[1] && refine[2] == o.refine[2];
+    }
+};
+
+std::mutex g_mesh_mu;
+std::vector<std::pair<MeshKey, std::shared_ptr<MeshBuffers>>> g_mesh_cache;   // most recently used last
+constexpr size_t kMeshCacheEntries = 4;
+
+int shared_mesh(const dsb_mesh &m, int device, double step_l, std::shared_ptr<MeshBuffers> &out)
+{
+    const char *env = getenv("DISIMPY_B200_MESH_CACHE");
+    const bool use_cache = !(env && env[0] == '0') && m.vertices && m.faces && m.xs && m.ys && m.zs && m.subvoxel_indices &&
+                           (m.triangle_indices || m.n_triangle_indices == 0) && m.n_faces > 0 && m.n_vertices > 0 &&
+                           m.n_sv[0] > 0 && m.n_sv[1] > 0 && m.n_sv[2] > 0 && m.n_sv[0] <= (1 << 20) && m.n_sv[1] <= (1 << 20) &&
+                           m.n_sv[2] <= (1 << 20) && m.n_triangle_indices >= 0;
+    MeshKey key;
+    if (use_cache) {
+        Range nvtx("dsb: mesh fingerprint");
+        key.device = device;
+        key.n_faces = m.n_faces, key.n_vertices = m.n_vertices, key.n_tri = m.n_triangle_indices;
+        for (int a = 0; a < 3; ++a) key.n_sv[a] = m.n_sv[a];
+        choose_refinement(m, step_l, m.n_triangle_indices, key.refine);
+        uint64_t h = fingerprint(m.vertices, sizeof(double) * 3 * (size_t)m.n_vertices, 1);
+        h = fingerprint(m.faces, sizeof(int64_t) * 3 * (size_t)m.n_faces, h);
+        h = fingerprint(m.xs, sizeof(double) * (size_t)(m.n_sv[0] + 1), h);
+        h = fingerprint(m.ys, sizeof(double) * (size_t)(m.n_sv[1] + 1), h);
+        h = fingerprint(m.zs, sizeof(double) * (size_t)(m.n_sv[2] + 1), h);
+        h = fingerprint(m.subvoxel_indices, sizeof(int64_t) * 2 * (size_t)(m.n_sv[0] * m.n_sv[1] * m.n_sv[2]), h);
+        if (m.n_triangle_indices > 0) h = fingerprint(m.triangle_indices, sizeof(int64_t) * (size_t)m.n_triangle_indices, h);
+        key.hash = h;
+        std::lock_guard<std::mutex> lk(g_mesh_mu);
+        for (size_t i = 0; i < g_mesh_cache.size(); ++i)
+            if (g_mesh_cache[i].first == key) {
+                out = g_mesh_cache[i].second;
+                std::rotate(g_mesh_cache.begin() + (long)i, g_mesh_cache.begin() + (long)i + 1, g_mesh_cache.end());
+                return DSB_OK;
+            }
+    }
+    std::shared_ptr<MeshBuffers> mb = std::make_shared<MeshBuffers>();
+    int rc = upload_mesh(m, *mb, step_l);
+    if (rc) return rc;
+    if (use_cache) {
+        std::lock_guard<std::mutex> lk(g_mesh_mu);
+        g_mesh_cache.emplace_back(key, mb);
+        if (g_mesh_cache.size() > kMeshCacheEntries) g_mesh_cache.erase(g_mesh_cache.begin());
+    }
+    out = mb;
+    return DSB_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------- the handle
@@ -811,7 +922,8 @@ struct dsb_sim {
     double *d_grad = nullptr, *d_grad_chunked = nullptr, *d_pos = nullptr, *d_phases = nullptr, *d_partials = nullptr, *d_signal = nullptr;
     unsigned long long *d_rng = nullptr, *d_rng0 = nullptr;
     unsigned char *d_exc = nullptr;
-    MeshBuffers mesh;
+    std::shared_ptr<MeshBuffers> mesh = std::make_shared<MeshBuffers>();   // possibly shared with other handles (shared_mesh)
+    double perm_prob = 0.0;
     dsb::EllipsoidConsts ell{};   // DSB_ELLIPSOID: semi-axes and what the distance check derives from them
     int rank = 0;            // > 0: low-rank protocol, the walk carries `rank` virtual measurements
     double *d_u = nullptr;   // (n_meas, rank) coefficients of the real measurements
@@ -991,6 +1103,10 @@ const char *dsb_last_error(void) { return g_err.c_str(); }
 
 int dsb_release_cache(void)
 {
+    {
+        std::lock_guard<std::mutex> mk(g_mesh_mu);
+        g_mesh_cache.clear();   // (meshes still used by live handles go when those are destroyed)
+    }
     std::lock_guard<std::mutex> lk(g_cache.mu);
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1044,7 +1160,7 @@ int dsb_destroy(dsb_sim *s)
     cache_free(s->fill_rng);
     cache_free(s->fill_pts);
     cache_free(s->fill_totals);
-    s->mesh.release();
+    s->mesh.reset();
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->stream2) cudaStreamDestroy(s->stream2);
     if (s->ev_rewind) cudaEventDestroy(s->ev_rewind);
@@ -1128,7 +1244,8 @@ static int create_impl(const dsb_params *params, const double *gradient, dsb_sim
     DSB_TRY(cudaStreamSynchronize(s->stream));  // the sources (caller's gradient, lr_u, lr_v) are free again
 #undef DSB_TRY
     if (params->substrate == DSB_MESH) {
-        rc = upload_mesh(params->mesh, s->mesh, params->step_l);
+        s->perm_prob = params->mesh.perm_prob;
+        rc = shared_mesh(params->mesh, params->device, params->step_l, s->mesh);
         if (rc) {
             std::string keep = g_err;
             dsb_destroy(s), *live = nullptr;
@@ -1242,7 +1359,8 @@ static int launch_walk_range(dsb_sim *s, cudaStream_t st, int64_t w0, int64_t w1
     kp.phases = s->d_phases;
     kp.iter_exc = s->d_exc;
     kp.partials = s->d_partials;
-    kp.mesh = s->mesh.dev;
+    kp.mesh = s->mesh->dev;
+    kp.mesh.perm_prob = s->perm_prob;   // (the upload may be shared with handles of another permeability)
     const int grid = (int)((w1 - w0 + dsb::kBlock - 1) / dsb::kBlock);
     cudaEvent_t e0, e1;
     DSB_CUDA(cudaEventCreate(&e0));
@@ -1606,7 +1724,7 @@ int dsb_fill_mesh_sim(dsb_sim *s, const double *voxel_size, int intra, uint64_t 
     if (e == cudaSuccess) e = cache_malloc(&d_pts, sizeof(double) * 3 * (size_t)n_points);
     if (e == cudaSuccess) e = cache_malloc(&d_totals, sizeof(int) * (size_t)(n_blocks + 1));
     int rc = e == cudaSuccess ? DSB_OK : fail(DSB_ENOMEM, cudaGetErrorString(e));
-    if (!rc) rc = build_fill_columns(s->mesh);
+    if (!rc) rc = build_fill_columns(*s->mesh);
     if (!rc) rc = launch_rng_init(s->prm.device, seed, 0, n_states, d_rng, s->stream);
     int64_t have = 0, proposed = 0;
     // One round per iteration like the reference's host loop (simulations.py:554-579): every thread
@@ -1630,7 +1748,7 @@ int dsb_fill_mesh_sim(dsb_sim *s, const double *voxel_size, int intra, uint64_t 
             const int chunk_blocks = (int)((want + dsb::kCompactBlock - 1) / dsb::kCompactBlock);
             double *pts = d_pts + 3 * c0;
             dsb::fill_mesh_kernel<<<(unsigned)((want + 127) / 128), 128, 0, s->stream>>>(
-                s->mesh.dev, s->mesh.columns, voxel_size[0], voxel_size[1], voxel_size[2], intra, (long long)want,
+                s->mesh->dev, s->mesh->columns, voxel_size[0], voxel_size[1], voxel_size[2], intra, (long long)want,
                 d_rng + c0, pts);
             dsb::fill_count_kernel<<<chunk_blocks, dsb::kCompactBlock, 0, s->stream>>>(pts, (long long)want, d_totals);
             dsb::fill_scan_kernel<<<1, 1024, 0, s->stream>>>(d_totals, chunk_blocks);
@@ -1683,7 +1801,7 @@ int dsb_fill_shard_begin(dsb_sim *s, uint64_t seed, int64_t thread_begin, int64_
     if (e == cudaSuccess) e = cache_malloc(&s->fill_pts, sizeof(double) * 3 * (size_t)n);
     if (e == cudaSuccess) e = cache_malloc(&s->fill_totals, sizeof(int) * (size_t)(n_blocks + 1));
     int rc = e == cudaSuccess ? DSB_OK : fail(DSB_ENOMEM, cudaGetErrorString(e));
-    if (!rc) rc = build_fill_columns(s->mesh);
+    if (!rc) rc = build_fill_columns(*s->mesh);
     if (!rc) rc = launch_rng_init(s->prm.device, seed, (uint64_t)thread_begin, n, s->fill_rng, s->stream);
     if (rc) {
         std::string keep = g_err;
@@ -1703,7 +1821,7 @@ int dsb_fill_shard_round(dsb_sim *s, const double *voxel_size, int intra, double
     const int64_t n = s->fill_t1 - s->fill_t0;
     const int n_blocks = (int)((n + dsb::kCompactBlock - 1) / dsb::kCompactBlock);
     dsb::fill_mesh_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(
-        s->mesh.dev, s->mesh.columns, voxel_size[0], voxel_size[1], voxel_size[2], intra, (long long)n, s->fill_rng,
+        s->mesh->dev, s->mesh->columns, voxel_size[0], voxel_size[1], voxel_size[2], intra, (long long)n, s->fill_rng,
         s->fill_pts);
     dsb::fill_count_kernel<<<n_blocks, dsb::kCompactBlock, 0, s->stream>>>(s->fill_pts, (long long)n, s->fill_totals);
     dsb::fill_scan_kernel<<<1, 1024, 0, s->stream>>>(s->fill_totals, n_blocks);
@@ -1916,6 +2034,163 @@ int dsb_simulate_multi(const dsb_params *params, const int32_t *devices, int32_t
             total_valid += valid[(size_t)k];
         }
         if (n_valid_out) *n_valid_out = total_valid;
+        return DSB_OK;
+    });
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------- the one collective, inside the library
+
+// NCCL is bound at run time (dlopen), so that the library neither links against it nor needs it for
+// single-GPU or device-list runs.  Only the five entry points the path needs.
+namespace {
+
+struct NcclUniqueId {
+    char internal[128];
+};
+
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string path;
+};
+
+std::mutex g_nccl_mu;
+NcclApi g_nccl;
+
+int nccl_api(const char *hint, NcclApi **out)
+{
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (!g_nccl.handle) {
+        std::vector<std::string> names;
+        if (const char *env = getenv("DISIMPY_B200_NCCL_LIB")) names.push_back(env);
+        if (hint && *hint) names.push_back(hint);
+        names.push_back("libnccl.so.2");
+        names.push_back("libnccl.so");
+        std::string tried;
+        for (const std::string &n : names) {
+            void *h = dlopen(n.c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (h) {
+                g_nccl.handle = h;
+                g_nccl.path = n;
+                break;
+            }
+            tried += n + "; ";
+        }
+        if (!g_nccl.handle) return fail(DSB_ESTATE, "NCCL library not found (tried " + tried + "set DISIMPY_B200_NCCL_LIB)");
+        g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(g_nccl.handle, "ncclGetUniqueId"));
+        g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(g_nccl.handle, "ncclCommInitRank"));
+        g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(g_nccl.handle, "ncclAllReduce"));
+        g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(g_nccl.handle, "ncclCommDestroy"));
+        g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.handle, "ncclGetErrorString"));
+        if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString) {
+            dlclose(g_nccl.handle);
+            g_nccl = NcclApi();
+            return fail(DSB_ESTATE, "NCCL library lacks an expected symbol");
+        }
+    }
+    *out = &g_nccl;
+    return DSB_OK;
+}
+
+#define DSB_NCCL(api, expr)                                                                            \
+    do {                                                                                               \
+        int r_ = (expr);                                                                               \
+        if (r_ != 0) return fail(DSB_ECUDA, std::string(#expr) + ": " + (api)->GetErrorString(r_));   \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int dsb_nccl_unique_id(const char *nccl_library, uint8_t id_out[128])
+{
+    if (!id_out) return fail(DSB_EINVAL, "null argument");
+    NcclApi *api = nullptr;
+    int rc = nccl_api(nccl_library, &api);
+    if (rc) return rc;
+    NcclUniqueId id;
+    DSB_NCCL(api, api->GetUniqueId(&id));
+    memcpy(id_out, id.internal, 128);
+    return DSB_OK;
+}
+
+int dsb_nccl_init(const char *nccl_library, int32_t device, int32_t rank, int32_t world_size, const uint8_t id[128],
+                  dsb_comm **out)
+{
+    if (!id || !out || world_size < 1 || rank < 0 || rank >= world_size) return fail(DSB_EINVAL, "bad arguments");
+    *out = nullptr;
+    NcclApi *api = nullptr;
+    int rc = nccl_api(nccl_library, &api);
+    if (rc) return rc;
+    DSB_CUDA(cudaSetDevice(device));
+    NcclUniqueId uid;
+    memcpy(uid.internal, id, 128);
+    void *comm = nullptr;
+    Range nvtx("dsb_nccl_init");
+    DSB_NCCL(api, api->CommInitRank(&comm, world_size, uid, rank));
+    *out = reinterpret_cast<dsb_comm *>(comm);
+    return DSB_OK;
+}
+
+int dsb_nccl_destroy(dsb_comm *comm)
+{
+    if (!comm) return DSB_OK;
+    NcclApi *api = nullptr;
+    int rc = nccl_api(nullptr, &api);
+    if (rc) return rc;
+    DSB_NCCL(api, api->CommDestroy(comm));
+    return DSB_OK;
+}
+
+int dsb_allreduce_signal(dsb_sim *s, dsb_comm *comm, double *signal, int64_t *n_valid)
+{
+    return guarded([&]() -> int {
+        if (!s || !comm || !signal) return fail(DSB_EINVAL, "null argument");
+        if (!s->finalized) return fail(DSB_ESTATE, "signal is available after the last time step only");
+        NcclApi *api = nullptr;
+        int rc = nccl_api(nullptr, &api);
+        if (rc) return rc;
+        Range nvtx("dsb_allreduce_signal: NCCL all-reduce + D2H");
+        DSB_CUDA(cudaSetDevice(s->prm.device));
+        const size_t count = (size_t)s->prm.n_meas + 1;
+        // in place on the handle's own result buffer and stream: ordered after the reduction kernel, no host detour
+        DSB_NCCL(api, api->AllReduce(s->d_signal, s->d_signal, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, s->stream));
+        std::vector<double> h(count);
+        DSB_CUDA(cudaMemcpyAsync(h.data(), s->d_signal, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        DSB_CUDA(cudaStreamSynchronize(s->stream));
+        memcpy(signal, h.data(), sizeof(double) * (size_t)s->prm.n_meas);
+        if (n_valid) *n_valid = (int64_t)llround(h.back());
+        return DSB_OK;
+    });
+}
+
+int dsb_allreduce_zeros(int32_t device, dsb_comm *comm, int64_t n_meas, double *signal, int64_t *n_valid)
+{
+    return guarded([&]() -> int {
+        if (!comm || !signal || n_meas <= 0) return fail(DSB_EINVAL, "bad arguments");
+        NcclApi *api = nullptr;
+        int rc = nccl_api(nullptr, &api);
+        if (rc) return rc;
+        DSB_CUDA(cudaSetDevice(device));
+        const size_t count = (size_t)n_meas + 1;
+        double *d = nullptr;
+        DSB_CUDA(cache_malloc(&d, count * sizeof(double)));
+        std::vector<double> h(count);
+        cudaError_t e = cudaMemset(d, 0, count * sizeof(double));
+        int nrc = 0;
+        if (e == cudaSuccess) nrc = api->AllReduce(d, d, count, 8, 0, comm, (cudaStream_t)0);
+        if (e == cudaSuccess && nrc == 0) e = cudaMemcpy(h.data(), d, count * sizeof(double), cudaMemcpyDeviceToHost);
+        cache_free(d);
+        if (nrc != 0) return fail(DSB_ECUDA, std::string("ncclAllReduce: ") + api->GetErrorString(nrc));
+        if (e != cudaSuccess) return fail(DSB_ECUDA, cudaGetErrorString(e));
+        memcpy(signal, h.data(), sizeof(double) * (size_t)n_meas);
+        if (n_valid) *n_valid = (int64_t)llround(h.back());
         return DSB_OK;
     });
 }

@@ -219,6 +219,69 @@ def _dist():
     return 0, 1, None
 
 
+_COMMS = {}   # (world, rank, device) -> library communicator (ctypes.c_void_p), or None when unavailable
+
+
+def _nccl_library_path():
+    """The NCCL the ranks should all load: the one bundled with torch when there is one (it is the
+    one torch.distributed itself runs on), else whatever the loader finds (libnccl.so.2)."""
+    try:
+        import nvidia.nccl
+        for base in list(getattr(nvidia.nccl, "__path__", [])):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return None
+
+
+def library_comm(dist, rank, world):
+    """The library's own NCCL communicator of this process for the path's one collective
+    (dsb_allreduce_signal), created on first use: rank 0 draws the NCCL unique id, torch.distributed
+    only carries its 128 bytes to the other ranks.  None (on every rank alike) when
+    DISIMPY_B200_NCCL=torch or when any rank failed to set it up: the caller then reduces through
+    torch.distributed."""
+    key = (world, rank, _device())
+    if key in _COMMS:
+        return _COMMS[key]
+    import torch
+    comm, ok = ctypes.c_void_p(), os.environ.get("DISIMPY_B200_NCCL", "") != "torch"
+    path = _nccl_library_path()
+    cpath = path.encode() if path else None
+    ident = np.zeros(128, dtype=np.uint8)
+    if ok and rank == 0:
+        ok = _lib.lib().dsb_nccl_unique_id(cpath, _lib.ptr(ident)) == 0
+    box = [ident.tobytes() if ok else None]
+    dist.broadcast_object_list(box, src=0)
+    ok = ok and box[0] is not None
+    if ok:
+        ident = np.frombuffer(box[0], dtype=np.uint8).copy()
+        ok = _lib.lib().dsb_nccl_init(cpath, _device(), rank, world, _lib.ptr(ident), ctypes.byref(comm)) == 0
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda:%d" % _device())
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)     # all ranks or none
+    if int(flag.item()) != 1:
+        if ok:
+            _lib.lib().dsb_nccl_destroy(comm)
+        comm = None
+    _COMMS[key] = comm
+    return comm
+
+
+def _destroy_comms():
+    for comm in _COMMS.values():
+        if comm:
+            try:
+                _lib.lib().dsb_nccl_destroy(comm)
+            except Exception:
+                pass
+    _COMMS.clear()
+
+
+import atexit  # noqa: E402
+atexit.register(_destroy_comms)
+
+
 def shard_range(n_walkers, rank, world_size):
     """Contiguous global walker range of a rank."""
     return n_walkers * rank // world_size, n_walkers * (rank + 1) // world_size
@@ -352,6 +415,12 @@ class Walk:
         n_valid = ctypes.c_int64(0)
         _lib.check(self._L.dsb_get_signal(self._h, _lib.ptr(sig), ctypes.byref(n_valid)),
                    "dsb_get_signal")
+        return sig, n_valid.value
+
+    def allreduce_signal(self, comm):
+        """Global (signal, valid count): NCCL all-reduce of the handle's result buffer inside the library."""
+        sig, n_valid = np.zeros(self.n_meas), ctypes.c_int64(0)
+        _lib.check(self._L.dsb_allreduce_signal(self._h, comm, _lib.ptr(sig), ctypes.byref(n_valid)), "dsb_allreduce_signal")
         return sig, n_valid.value
 
     def copy_signal_to(self, dev_ptr):
@@ -723,8 +792,22 @@ class _Shards:
         handles summed in slot order, then one all-reduce over the ranks."""
         total = np.zeros(self.n_meas + 1)
         live = self.live()
-        if self.dist is not None and self.dist.get_backend() == "nccl":
-            # the library copies its (n_meas + 1) result doubles into the tensor NCCL reduces in place
+        comm = library_comm(self.dist, self.rank, self.world) if (
+            self.dist is not None and self.dist.get_backend() == "nccl") else None
+        if comm:
+            # the library reduces its own result buffer over the ranks (NCCL, in place, on its stream)
+            sig, n_valid = np.zeros(self.n_meas), ctypes.c_int64(0)
+            if live:
+                _lib.check(_lib.lib().dsb_allreduce_signal(live[0][0]._h, comm, _lib.ptr(sig), ctypes.byref(n_valid)),
+                           "dsb_allreduce_signal")
+            else:
+                _lib.check(_lib.lib().dsb_allreduce_zeros(_device(), comm, self.n_meas, _lib.ptr(sig), ctypes.byref(n_valid)),
+                           "dsb_allreduce_zeros")
+            total[:-1], total[-1] = sig, n_valid.value
+            if trace:
+                trace("walk finished + all-reduce")
+        elif self.dist is not None and self.dist.get_backend() == "nccl":
+            # (fallback: torch.distributed reduces a tensor the library copies its result doubles into)
             import torch
             t = torch.zeros(self.n_meas + 1, dtype=torch.float64, device="cuda:%d" % _device())
             if live:
