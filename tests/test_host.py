@@ -512,3 +512,19 @@ def test_part_edges_and_device_list(monkeypatch):
     rows = S._assemble_rows([([(0, 2, 0), (4, 5, 2)], np.array([[0.0], [1.0], [4.0]])),
                              ([(2, 4, 0)], np.array([[2.0], [3.0]]))], 5, None)
     assert np.array_equal(rows[:, 0], np.arange(5.0))
+
+
+def test_library_binds_nccl_at_run_time():
+    """The path's one collective lives in the library (dsb_allreduce_signal); NCCL is bound by dlopen,
+    so drawing a unique id needs no GPU -- and a missing NCCL is an error code with a text, not a crash."""
+    import ctypes
+    from disimpy_b200 import _lib, simulations
+    L = _lib.lib()
+    ident = np.zeros(128, dtype=np.uint8)
+    path = simulations._nccl_library_path()
+    rc = L.dsb_nccl_unique_id(path.encode() if path else None, _lib.ptr(ident))
+    if rc == 0:
+        assert ident.any()
+    else:
+        assert rc == 4 and b"NCCL" in L.dsb_last_error()
+    assert L.dsb_nccl_init(None, 0, 3, 2, _lib.ptr(ident), ctypes.byref(ctypes.c_void_p())) == 1   # rank >= world: EINVAL
