@@ -612,6 +612,10 @@ def main():
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
             "signal": float(signal), "n_valid": int(n_valid),
             "mesh": mesh, "e2e_default_verbose_call": verbose_e2e,
+            # the mesh half of BASELINE.json's metric as plain numbers (whole-job walker-steps/s through simulation() on
+            # every rank): config 4 at 1e6 walkers per GPU, config 5 at 1.25e7 per GPU (8 GPUs = its full 1e8 walkers)
+            "mesh_config4_value": next((m.get("value") for m in (mesh or []) if m.get("config") == "config4"), None),
+            "mesh_config5_value": next((m.get("value") for m in (mesh or []) if m.get("config") == "config5"), None),
             "other_workloads": secondary, "baselines": baselines,
         }
         sys.stdout.flush()

@@ -1206,7 +1206,8 @@ static int create_impl(const dsb_params *params, const double *gradient, dsb_sim
     // measurements and are expanded at the end; DISIMPY_B200_LOWRANK=0 keeps the general path.
     std::vector<double> lr_u, lr_v;
     const char *lr_env = getenv("DISIMPY_B200_LOWRANK");
-    if (M > dsb::kMaxRegMeas && !(lr_env && lr_env[0] == '0') &&
+    // (the factorisation works on a copy of the whole gradient: not attempted above 1 GiB of it)
+    if (M > dsb::kMaxRegMeas && !(lr_env && lr_env[0] == '0') && M * 3 * T <= (int64_t(1) << 27) &&
         factor_low_rank(gradient, M, 3 * T, (int)std::min<int64_t>(dsb::kMaxRank, M / 2), lr_u, lr_v, s->rank)) {
         gradient = lr_v.data();  // (a rank above M / 2 would not pay for the expansion)
     } else {

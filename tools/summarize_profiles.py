@@ -52,7 +52,7 @@ def launches_md(tag, path):
         a[0] += 1
         a[1] += float(r["Metric Value"].replace(",", "")) / 1e6
     tot = sum(v[1] for v in agg.values())
-    out = ["# %s: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-secondary` (1 B200)" % tag,
+    out = ["# %s: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-secondary --no-mesh --no-reference-baselines` (1 B200)" % tag,
            "# per-launch times are cold-cache and serialised under the profiler: compare SHARES", "",
            "| kernel | launches | total ms | share |", "|---|---|---|---|"]
     for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
