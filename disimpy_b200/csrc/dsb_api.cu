@@ -1937,6 +1937,18 @@ int dsb_fill_mesh_multi(dsb_sim **sims, int32_t n_sims, const double *voxel_size
                 if (rcs[(size_t)k]) return fail(rcs[(size_t)k], errs[(size_t)k]);
             return (int)DSB_OK;
         };
+        // accepted points travel device to device: direct peer access where the hardware offers it (NVLink /
+        // NVSwitch on a B200 node); without it cudaMemcpyPeerAsync stages through the host
+        for (int d = 0; d < n_sims; ++d)
+            for (int r = 0; r < n_sims; ++r) {
+                const int dd = sims[d]->prm.device, dr = sims[r]->prm.device;
+                int can = 0;
+                if (dd != dr && cudaDeviceCanAccessPeer(&can, dd, dr) == cudaSuccess && can) {
+                    cudaSetDevice(dd);
+                    cudaDeviceEnablePeerAccess(dr, 0);   // (cudaErrorPeerAccessAlreadyEnabled from an earlier call is fine)
+                    cudaGetLastError();
+                }
+            }
         int rc = on_all([&](int k) -> int {
             int r = dsb_fill_shard_begin(sims[k], seed, w0[(size_t)k], w1[(size_t)k]);
             if (r) return r;
