@@ -812,7 +812,7 @@ int build_fill_columns(MeshBuffers &mb)
 // simulation() is usually called many times on one substrate (other protocols, other seeds), and each
 // call hands the library the same mesh arrays again.  Re-laying them out, uploading them and refining
 // the search grid costs 12 ms for the 1e5-triangle mesh of BASELINE config 4 next to a 97 ms walk, 70
-// ms for the 1e6-triangle mesh.  The last uploads are therefore kept per device, found again by a
+// ms for the 1e6-triangle mesh.  The last uploads (four per device) are therefore kept, found again by a
 // 64-bit fingerprint of every input array (plus sizes and the refinement the step length asks for),
 // and shared by the handles that use them.  DISIMPY_B200_MESH_CACHE=0 turns this off.
 uint64_t fingerprint(const void *data, size_t bytes, uint64_t seed)
@@ -897,7 +897,16 @@ int shared_mesh(const dsb_mesh &m, int device, double step_l, std::shared_ptr<Me
     if (use_cache) {
         std::lock_guard<std::mutex> lk(g_mesh_mu);
         g_mesh_cache.emplace_back(key, mb);
-        if (g_mesh_cache.size() > kMeshCacheEntries) g_mesh_cache.erase(g_mesh_cache.begin());
+        // at most kMeshCacheEntries per DEVICE (a device list uploads the same mesh once per device): drop that
+        // device's least recently used one
+        size_t on_device = 0;
+        for (const auto &e : g_mesh_cache) on_device += e.first.device == key.device;
+        if (on_device > kMeshCacheEntries)
+            for (auto it = g_mesh_cache.begin(); it != g_mesh_cache.end(); ++it)
+                if (it->first.device == key.device) {
+                    g_mesh_cache.erase(it);
+                    break;
+                }
     }
     out = mb;
     return DSB_OK;
