@@ -557,8 +557,8 @@ def main():
     if not args.no_mesh:
         mesh = mesh_e2e_all_ranks(world, rank, dist if world > 1 else None, torch)
 
-    # the default call of the public API shows progress (quiet=False): a handful of launches
-    # instead of the part-by-part pipeline; timed once so that the path users hit first is on record
+    # the default call of the public API shows progress (quiet=False); timed once so that the path users
+    # hit first is on record
     verbose_e2e = None
     if rank == 0 and world == 1 and not args.no_e2e:
         import contextlib
@@ -567,7 +567,7 @@ def main():
             t0 = time.perf_counter()
             simulations.simulation(n_global, DIFFUSIVITY, g, dt, sub, seed=SEED)
             verbose_e2e = {"value": units_per_step / (time.perf_counter() - t0), "unit": UNIT,
-                           "note": "simulation(..., quiet=False): positions drawn first, ~20 launches with progress output"}
+                           "note": "simulation(..., quiet=False), the default call: same part-by-part pipeline, with the progress line"}
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

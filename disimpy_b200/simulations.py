@@ -586,9 +586,10 @@ def simulation(
         print("Step duration = %s s" % dt)
 
     # Analytic substrates draw their initial positions from one sequential host stream.  When
-    # nothing needs all of them up front (no trajectory file, no progress display) they are
-    # drawn part by part while the GPU already walks the earlier parts.
-    pipelined = substrate.type in ("sphere", "cylinder", "ellipsoid") and not traj and quiet
+    # nothing needs all of them up front (no trajectory file) they are drawn part by part while
+    # the GPU already walks the earlier parts (the progress display then counts walkers, not
+    # time steps).
+    pipelined = substrate.type in ("sphere", "cylinder", "ellipsoid") and not traj
     positions = None
     device_fill = False
     if pipelined:
@@ -630,7 +631,7 @@ def simulation(
         if traj and rank == 0 and not device_fill:
             _write_traj(traj, "w", positions)
         if pipelined:
-            _walk_pipelined(shards, substrate, seed, trace)
+            _walk_pipelined(shards, substrate, seed, trace, progress=not quiet and rank == 0)
         elif device_fill:
             shards.fill_mesh(substrate, seed, cuda_bs)
             if traj:
@@ -886,7 +887,7 @@ def _position_parts(substrate, lo, hi, seed, part=_PART, wanted=None):
         sampler.close()
 
 
-def _walk_pipelined(shards, substrate, seed, trace=None):
+def _walk_pipelined(shards, substrate, seed, trace=None, progress=False):
     """Walks every part over all time steps as soon as its positions are there: the host draws
     the next part while the GPUs work.  Same positions, same walk, same signal as drawing
     everything first.  One pass over the sequential stream serves every local handle; stretches
@@ -904,11 +905,15 @@ def _walk_pipelined(shards, substrate, seed, trace=None):
     sampler, finish = _stream_sampler(substrate, seed)
     try:
         at = 0
+        todo, done = max(sum(b - a for a, b, _, _ in jobs), 1), 0
         for k, (a, b, w, la) in enumerate(jobs):
+            if progress:   # the reference's progress line (simulations.py:1209), by walkers handed to the GPU
+                sys.stdout.write(f"\r{np.round((done / todo) * 100, 1)}%")
+                sys.stdout.flush()
             sampler.skip(a - at)
             w.set_positions_part(la, la + b - a, finish(sampler.next(b - a)))
             w.run_part(la, la + b - a)
-            at = b
+            at, done = b, done + b - a
             if trace and k == 0:
                 trace("first part submitted")
     finally:
