@@ -456,7 +456,7 @@ def main():
         walk.run(0, N_T)
         if world > 1 and comm:
             sig, n_valid = walk.allreduce_signal(comm)   # the one collective of the path: NCCL all-reduce inside the
-            return sig[0], n_valid                       # library, in place on its result buffer and stream; 16 bytes D2H
+            return sig[0], n_valid                       # library, from its result buffer, on its stream; 16 bytes D2H
         if world > 1:
             walk.copy_signal_to(sig_buf.data_ptr())   # (fallback through torch.distributed)
             dist.all_reduce(sig_buf)

@@ -1227,7 +1227,7 @@ static int create_impl(const dsb_params *params, const double *gradient, dsb_sim
     DSB_TRY(cache_malloc(&s->d_pos, sizeof(double) * 3 * N));
     DSB_TRY(cache_malloc(&s->d_phases, sizeof(double) * Mw * N));
     DSB_TRY(cache_malloc(&s->d_partials, sizeof(double) * (M + 1) * s->grid));
-    DSB_TRY(cache_malloc(&s->d_signal, sizeof(double) * (M + 1)));
+    DSB_TRY(cache_malloc(&s->d_signal, sizeof(double) * 2 * (M + 1)));   // this shard's result, then room for the all-reduced one
     DSB_TRY(cache_malloc(&s->d_rng, sizeof(unsigned long long) * 2 * N));
     DSB_TRY(cache_malloc(&s->d_rng0, sizeof(unsigned long long) * 2 * N));
     DSB_TRY(cache_malloc(&s->d_exc, N));
@@ -2181,10 +2181,12 @@ int dsb_allreduce_signal(dsb_sim *s, dsb_comm *comm, double *signal, int64_t *n_
         Range nvtx("dsb_allreduce_signal: NCCL all-reduce + D2H");
         DSB_CUDA(cudaSetDevice(s->prm.device));
         const size_t count = (size_t)s->prm.n_meas + 1;
-        // in place on the handle's own result buffer and stream: ordered after the reduction kernel, no host detour
-        DSB_NCCL(api, api->AllReduce(s->d_signal, s->d_signal, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, s->stream));
+        // from the handle's own result buffer, on its stream: ordered after the reduction kernel, no host detour
+        // (out of place, next to it: the shard's own result stays what dsb_get_signal returns, and the call can be repeated)
+        double *global = s->d_signal + count;
+        DSB_NCCL(api, api->AllReduce(s->d_signal, global, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, s->stream));
         std::vector<double> h(count);
-        DSB_CUDA(cudaMemcpyAsync(h.data(), s->d_signal, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        DSB_CUDA(cudaMemcpyAsync(h.data(), global, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
         DSB_CUDA(cudaStreamSynchronize(s->stream));
         memcpy(signal, h.data(), sizeof(double) * (size_t)s->prm.n_meas);
         if (n_valid) *n_valid = (int64_t)llround(h.back());
