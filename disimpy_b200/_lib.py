@@ -70,7 +70,7 @@ EXPORTS = [
     "dsb_rewind", "dsb_set_positions_part", "dsb_run_part", "dsb_finish", "dsb_release_cache",
     "dsb_set_rng_states", "dsb_fill_mesh_sim", "dsb_protocol_rank", "dsb_protocol_factor", "dsb_set_rng_part", "dsb_host_sampler_create", "dsb_host_sampler_next", "dsb_host_sampler_destroy",
     "dsb_fill_shard_begin", "dsb_fill_shard_round", "dsb_fill_shard_end",
-    "dsb_copy_signal_dev", "dsb_simulate_multi", "dsb_fill_mesh_multi", "dsb_selftest_sqrt",
+    "dsb_copy_signal_dev", "dsb_simulate_multi", "dsb_fill_mesh_multi", "dsb_selftest_sqrt", "dsb_measure_l2_peak",
     "dsb_nccl_unique_id", "dsb_nccl_init", "dsb_allreduce_signal", "dsb_allreduce_zeros", "dsb_nccl_destroy",
 ]
 
@@ -109,6 +109,7 @@ def lib():
         L.dsb_timer_start.argtypes = [ctypes.c_void_p]
         L.dsb_timer_stop.argtypes = [ctypes.c_void_p, c_double_p]
         L.dsb_measure_fp64_peak.argtypes = [ctypes.c_int32, c_double_p]
+        L.dsb_measure_l2_peak.argtypes = [ctypes.c_int32, c_double_p]
         L.dsb_simulate.argtypes = [ctypes.POINTER(DsbParams)] + [ctypes.c_void_p] * 3 + [
             c_int64_p] + [ctypes.c_void_p] * 3
         L.dsb_rng_states.argtypes = [ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64,

@@ -1632,6 +1632,43 @@ int dsb_measure_fp64_peak(int32_t device, double *dfma_per_second)
     return DSB_OK;
 }
 
+int dsb_measure_l2_peak(int32_t device, double *bytes_per_second)
+{
+    if (!bytes_per_second) return fail(DSB_EINVAL, "null argument");
+    DSB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DSB_CUDA(cudaGetDeviceProperties(&prop, device));
+    // a third of the L2: resident whatever the hashing over the two dies does
+    const size_t bytes = std::max<size_t>((size_t)prop.l2CacheSize / 3, size_t(8) << 20) / 16 * 16;
+    uint4 *d_buf = nullptr;
+    unsigned *d_out = nullptr;
+    DSB_CUDA(cudaMalloc(&d_buf, bytes));
+    DSB_CUDA(cudaMalloc(&d_out, sizeof(unsigned)));
+    DSB_CUDA(cudaMemset(d_buf, 1, bytes));
+    cudaEvent_t e0, e1;
+    DSB_CUDA(cudaEventCreate(&e0));
+    DSB_CUDA(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, passes = 40;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        DSB_CUDA(cudaEventRecord(e0));
+        dsb::l2_peak_kernel<<<blocks, 256>>>(d_buf, (long long)(bytes / 16), passes, d_out);
+        DSB_CUDA(cudaEventRecord(e1));
+        DSB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        DSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = (double)bytes * passes / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_buf);
+    cudaFree(d_out);
+    DSB_CUDA(cudaGetLastError());
+    *bytes_per_second = best;
+    return DSB_OK;
+}
+
 int dsb_selftest_sqrt(int32_t device, uint64_t seed, int32_t exp_lo, int32_t exp_hi, int64_t n, int64_t *n_mismatch,
                       double *first_mismatch)
 {

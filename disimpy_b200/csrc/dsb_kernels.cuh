@@ -1272,6 +1272,23 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
     out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = sum;
 }
 
+// ---------------------------------------------------------------- L2 bandwidth probe
+
+// Every thread streams 16-byte loads over a buffer that fits the L2 (the host sizes it), again and again:
+// after the first pass the bytes come from L2.  Its rate is the L2 -> SM ceiling the mesh roofline of
+// bench.py is quoted against (measured here instead of taken from a document).
+__global__ void __launch_bounds__(256) l2_peak_kernel(const uint4 *buf, long long n_vec, int passes, unsigned *out)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned acc = 0u;
+    for (int pass = 0; pass < passes; ++pass)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+            const uint4 v = __ldcg(buf + i);
+            acc ^= v.x ^ v.y ^ v.z ^ v.w;
+        }
+    if (acc == 0x12345678u) out[0] = acc;   // (keeps the loads alive)
+}
+
 // ---------------------------------------------------------------- ellipsoid constants
 
 __global__ void ellipsoid_consts_kernel(double a0, double a1, double a2, EllipsoidConsts *out)
