@@ -2060,6 +2060,7 @@ int dsb_simulate_multi(const dsb_params *params, const int32_t *devices, int32_t
         std::vector<std::thread> pool;
         for (int k = 0; k < n_used; ++k)
             pool.emplace_back([&, k] {
+                try {
                 const int64_t lo = N * k / n_used, hi = N * (k + 1) / n_used;
                 dsb_params p = *params;
                 p.device = devices[k];
@@ -2082,10 +2083,13 @@ int dsb_simulate_multi(const dsb_params *params, const int32_t *devices, int32_t
                 if (rc) errs[(size_t)k] = g_err;
                 rcs[(size_t)k] = rc;
                 dsb_destroy(s);
+                } catch (...) {   // (an exception must not leave a host thread: std::terminate)
+                    rcs[(size_t)k] = DSB_ENOMEM;
+                }
             });
         for (auto &th : pool) th.join();
         for (int k = 0; k < n_used; ++k)
-            if (rcs[(size_t)k]) return fail(rcs[(size_t)k], errs[(size_t)k]);
+            if (rcs[(size_t)k]) return fail(rcs[(size_t)k], errs[(size_t)k].empty() ? "host allocation failed" : errs[(size_t)k]);
         int64_t total_valid = 0;
         for (int64_t m = 0; m < M; ++m) signal_out[m] = 0.0;
         for (int k = 0; k < n_used; ++k) {   // fixed order: the sum does not depend on which device finished first
