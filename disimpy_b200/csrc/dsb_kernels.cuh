@@ -33,11 +33,14 @@ constexpr int kMaxRank = 16;         // largest rank of a protocol walked throug
 // Steps per chunk of the many-measurement kernels (n_meas > kMaxRegMeas): every phase makes one
 // round trip through HBM per chunk, so longer chunks mean less traffic (16 n_meas / chunk bytes
 // per walker-step); the mesh kernel's shared memory leaves room for 8 steps only.
+#ifndef DSB_CHUNK
+#define DSB_CHUNK 16   // analytic substrates (a multiple of 4)
+#endif
 template <int SUB>
 struct ChunkSteps {
-    static constexpr int value = SUB == 4 ? 8 : 16;
+    static constexpr int value = SUB == 4 ? 8 : DSB_CHUNK;
 };
-__host__ __device__ constexpr int chunk_steps(int substrate) { return substrate == 4 ? 8 : 16; }
+__host__ __device__ constexpr int chunk_steps(int substrate) { return substrate == 4 ? 8 : DSB_CHUNK; }
 __host__ __device__ constexpr int grad_row_len(int chunk) { return 3 * chunk + 4; }  // + padding (bank spread)
 #ifndef DSB_GRADROWS
 #define DSB_GRADROWS 8
