@@ -887,33 +887,36 @@ def _stream_sampler(substrate, seed):
     else:
         sampler, to_lab = _HostSampler(2, seed, substrate.semiaxes, 3), substrate.R
 
-    def finish(pts):
+    def finish(pts, alone=False):
         if substrate.type == "cylinder":
             body = np.zeros((len(pts), 3))
             body[:, 1:3] = pts
             pts = body
         if to_lab is not None:
-            pts = np.matmul(to_lab, pts.T).T
+            if len(pts) == 1 and not alone:
+                # BLAS multiplies a single column through another routine (gemv) than a matrix (gemm), with a
+                # last-bit difference: a one-walker stretch of a longer run must round like the reference's product
+                # over all walkers, so it is multiplied as a two-column matrix
+                pts = np.matmul(to_lab, np.vstack([pts, pts]).T).T[:1]
+            else:
+                pts = np.matmul(to_lab, pts.T).T
         return pts
     return sampler, finish
 
 
-def _position_parts(substrate, lo, hi, seed, part=_PART, wanted=None):
-    """Initial positions of global walkers [lo, hi) of an analytic substrate, part by part:
-    yields (a, b, positions of local walkers [a, b)).  Concatenated, the parts are what
-    _fill_sphere / _initial_positions_cylinder / _initial_positions_ellipsoid return in one go
-    (simulations.py:346-418).  Parts for which ``wanted(a, b)`` is false are drawn (the stream is
-    sequential) but not yielded."""
+def _stream_stretches(substrate, seed, stretches, n_total=None):
+    """Initial positions of the global walkers [a, b) of every (a, b) in ``stretches`` (ascending, disjoint),
+    from ONE pass over the sequential host stream: yields one (b - a, 3) array per stretch.  Concatenated
+    over [0, n) they are what _fill_sphere / _initial_positions_cylinder / _initial_positions_ellipsoid
+    return in one go (simulations.py:346-418); walkers between the stretches are drawn and dropped.  ``n_total``:
+    the number of walkers of the whole run (a run of ONE walker rotates its position like the reference does)."""
     sampler, finish = _stream_sampler(substrate, seed)
     try:
-        sampler.skip(lo)
-        n = hi - lo
-        for a in range(0, n, part):
-            b = min(a + part, n)
-            pts = sampler.next(b - a)
-            if wanted is not None and not wanted(a, b):
-                continue
-            yield a, b, finish(pts)
+        at = 0
+        for a, b in stretches:
+            sampler.skip(a - at)
+            yield finish(sampler.next(b - a), alone=n_total == 1)
+            at = b
     finally:
         sampler.close()
 
@@ -933,22 +936,18 @@ def _walk_pipelined(shards, substrate, seed, trace=None, progress=False):
             edges = part_edges(hi - lo)
             jobs += [(lo + a, lo + b, w, a) for a, b in zip(edges[:-1], edges[1:])]
     jobs.sort(key=lambda j: j[0])
-    sampler, finish = _stream_sampler(substrate, seed)
-    try:
-        at = 0
-        todo, done = max(sum(b - a for a, b, _, _ in jobs), 1), 0
-        for k, (a, b, w, la) in enumerate(jobs):
-            if progress:   # the reference's progress line (simulations.py:1209), by walkers handed to the GPU
-                sys.stdout.write(f"\r{np.round((done / todo) * 100, 1)}%")
-                sys.stdout.flush()
-            sampler.skip(a - at)
-            w.set_positions_part(la, la + b - a, finish(sampler.next(b - a)))
-            w.run_part(la, la + b - a)
-            at, done = b, done + b - a
-            if trace and k == 0:
-                trace("first part submitted")
-    finally:
-        sampler.close()
+    todo, done = max(sum(b - a for a, b, _, _ in jobs), 1), 0
+    stretches = _stream_stretches(substrate, seed, [(a, b) for a, b, _, _ in jobs], shards.n_walkers)
+    for k, (a, b, w, la) in enumerate(jobs):
+        if progress:   # the reference's progress line (simulations.py:1209), by walkers handed to the GPU
+            sys.stdout.write(f"\r{np.round((done / todo) * 100, 1)}%")
+            sys.stdout.flush()
+        w.set_positions_part(la, la + b - a, next(stretches))
+        w.run_part(la, la + b - a)
+        done += b - a
+        if trace and k == 0:
+            trace("first part submitted")
+    stretches.close()
     for w, _ in shards.live():
         w.finish()
 
@@ -1031,9 +1030,3 @@ def _assemble_rows(pieces, n_total, dist):
             full[a:b] = rows[la:la + b - a]
     return full
 
-
-def _gather_rows(local, n_total, owned, dist):
-    """Assemble per-walker rows from all ranks (only used for final_pos / all_signals / traj
-    / the iter_exc warning -- per-shard host gathers, no device collective).  ``owned``: this
-    rank's walkers as owned_ranges returns them."""
-    return _assemble_rows([(owned, local)], n_total, dist)

@@ -301,7 +301,7 @@ pos0 = O.initial_positions(sub, n, 9)
 part = O.run_walk(sub, grad, 1e-4, 2e-9, pos0[lo:hi], seed=9, walker_offset=lo)
 sig = O.signals_from_phases(part["phases"], part["iter_exc"])
 total = simulations._allreduce_sum(sig, d)
-allpos = simulations._gather_rows(part["positions"], n, simulations.owned_ranges(n, rank, world), d)
+allpos = simulations._assemble_rows([(simulations.owned_ranges(n, rank, world), part["positions"])], n, d)
 full = O.run_walk(sub, grad, 1e-4, 2e-9, pos0, seed=9)
 assert np.array_equal(allpos, full["positions"])
 assert np.allclose(total, O.signals_from_phases(full["phases"], full["iter_exc"]), rtol=1e-13)
@@ -315,7 +315,7 @@ for a, b, la in owned:
     piece = O.run_walk(sub, grad, 1e-4, 2e-9, pos0[a:b], seed=9, walker_offset=a)
     rows[la:la + b - a] = piece["positions"]
     sig2 += O.signals_from_phases(piece["phases"], piece["iter_exc"])
-assert np.array_equal(simulations._gather_rows(rows, n, owned, d), full["positions"])
+assert np.array_equal(simulations._assemble_rows([(owned, rows)], n, d), full["positions"])
 assert np.allclose(simulations._allreduce_sum(sig2, d), O.signals_from_phases(full["phases"], full["iter_exc"]), rtol=1e-13)
 dist.destroy_process_group()
 print("rank", rank, "ok")
@@ -355,10 +355,13 @@ def test_position_parts_equal_one_shot_sampling():
         else:
             full = simulations._initial_positions_ellipsoid(n, sub.semiaxes, sub.R, 9)
         for lo, hi in ((0, n), (123_457, n)):
-            parts = list(simulations._position_parts(sub, lo, hi, 9, part=65_536))
-            assert [a for a, _, _ in parts] == list(range(0, hi - lo, 65_536))
-            got = np.vstack([pts for _, _, pts in parts])
+            edges = list(range(lo, hi, 65_536)) + [hi]
+            got = np.vstack(list(simulations._stream_stretches(sub, 9, list(zip(edges[:-1], edges[1:])))))
             assert np.array_equal(got, full[lo:hi]), sub.type
+        # stretches with gaps (a rank's round-robin parts): the walkers in between are drawn and dropped
+        picked = [(0, 1000), (5000, 70_000), (200_000, 200_001)]
+        for (a, b), pts in zip(picked, simulations._stream_stretches(sub, 9, picked)):
+            assert np.array_equal(pts, full[a:b]), sub.type
 
 
 def test_round_robin_parts_cover_all_walkers():
