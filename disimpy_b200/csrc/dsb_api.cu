@@ -377,6 +377,7 @@ struct MeshBuffers {
     int2 *f_cell_rng = nullptr;
     double *f_xs = nullptr, *f_ys = nullptr, *f_zs = nullptr;
     int refine[3] = {1, 1, 1};
+    int64_t data_bytes = 0, grid_bytes = 0;   // triangles + normals; list entries + cell ranges of the grid the walk searches
     std::mutex mu;   // the sampler's column lists are built on first use; handles may share one upload
     MeshBuffers() = default;
     MeshBuffers(const MeshBuffers &) = delete;
@@ -547,6 +548,7 @@ int build_search_grid(const dsb_mesh &m, const HostBuf<int2> &cells, const HostB
     DSB_CUDA(cudaMemcpy(mb.f_ys, fb[1].data(), fb[1].size() * sizeof(double), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaMemcpy(mb.f_zs, fb[2].data(), fb[2].size() * sizeof(double), cudaMemcpyHostToDevice));
     DSB_CUDA(cudaDeviceSynchronize());  // (pageable sources, see upload_mesh)
+    mb.grid_bytes = (int64_t)(fentry.size() * sizeof(uint4) + fcells.size() * sizeof(int2));
     dsb::SearchGrid &g = mb.dev.fine;
     g.entry = mb.f_entry;
     g.cell_rng = mb.f_cell_rng;
@@ -680,6 +682,8 @@ int upload_mesh(const dsb_mesh &m, MeshBuffers &mb, double step_l = 0.0)
     // copies from pageable memory may return before the DMA lands, and the handle's streams do not
     // synchronise with the legacy stream: wait here
     DSB_CUDA(cudaDeviceSynchronize());
+    mb.data_bytes = (int64_t)(tri.size() * sizeof(double) + sizeof(double) * 3 * (size_t)m.n_faces);
+    mb.grid_bytes = (int64_t)(entry.size() * sizeof(uint4) + cells.size() * sizeof(int2));
     dsb::MeshDev &d = mb.dev;
     d.tri = mb.tri;
     d.normal = mb.normal;
@@ -934,6 +938,10 @@ struct dsb_sim {
     std::shared_ptr<MeshBuffers> mesh = std::make_shared<MeshBuffers>();   // possibly shared with other handles (shared_mesh)
     double perm_prob = 0.0;
     dsb::EllipsoidConsts ell{};   // DSB_ELLIPSOID: semi-axes and what the distance check derives from them
+    // mesh walk with the walkers in cell order (resort_interval, sort_walkers); allocated at the first sort
+    int *d_order = nullptr, *d_key = nullptr, *d_bins = nullptr;
+    dsb::CellBins bins{};
+    bool signal_from_phases = false;   // the launch that reached the last step left the signal partials to phases_signal_kernel
     int rank = 0;            // > 0: low-rank protocol, the walk carries `rank` virtual measurements
     double *d_u = nullptr;   // (n_meas, rank) coefficients of the real measurements
     int64_t t_cur = -1;  // -1: positions not set
@@ -1166,6 +1174,9 @@ int dsb_destroy(dsb_sim *s)
     cache_free(s->d_rng);
     cache_free(s->d_rng0);
     cache_free(s->d_exc);
+    cache_free(s->d_order);
+    cache_free(s->d_key);
+    cache_free(s->d_bins);
     cache_free(s->fill_rng);
     cache_free(s->fill_pts);
     cache_free(s->fill_totals);
@@ -1340,8 +1351,75 @@ int dsb_set_positions_dev(dsb_sim *s, const double *positions_dev)
     return rewind_sim(s);
 }
 
-// one launch of the walk kernel: walkers [w0, w1) over time steps [t0, t1)
-static int launch_walk_range(dsb_sim *s, cudaStream_t st, int64_t w0, int64_t w1, int64_t t0, int64_t t1)
+#ifndef DSB_RESORT_MIN_WALKERS
+#define DSB_RESORT_MIN_WALKERS 65536
+#endif
+#ifndef DSB_RESORT_MIN_MESH_BYTES
+#define DSB_RESORT_MIN_MESH_BYTES (int64_t(64) << 20)   // half the L2: a smaller mesh stays resident whatever the order
+#endif
+#ifndef DSB_RESORT_DRIFT
+#define DSB_RESORT_DRIFT 0.1   // of the voxel edge: rms drift per axis after which the walkers are sorted again
+#endif
+// A mesh walk advances its walkers in cell order (sort_walkers): 0 = no (index order), otherwise
+// the number of steps after which a run sorts them again.  Measured on a B200
+// (profiles/r02_ab_kbench_cell_order.txt): what pays is the L2, not the L1 -- with the walkers of
+// the ~600 resident blocks in one slab of the mesh instead of all over it, the 1e6-triangle mesh of
+// BASELINE config 5 (178 MB of lists and triangles against 126 MB of L2) walks 17-18 % faster, the
+// 1e5-triangle mesh of config 4 (L2-resident anyway) +0.7 % from uniform initial positions and -1.9 %
+// from extra-axonal ones (bench.py), hence the size test below; sorting again every 16-128 steps to keep
+// the lanes of a WARP in the same cell is slower than not sorting at all (-20 % ... -4 %): every
+// launch ends with its lanes draining one by one, ~4 steps' worth of time.  So: once at the start of
+// a run, and again only when diffusion has spread a block's walkers over a good part of the voxel.
+// Register phases only (the many-measurement kernel needs consecutive walkers for its tiles).
+// DISIMPY_B200_RESORT=<steps> overrides the interval, 0 turns the sort off.
+static int64_t resort_interval(const dsb_sim *s)
+{
+    const dsb_params &P = s->prm;
+    if (P.substrate != DSB_MESH) return 0;
+    const int meas = s->rank > 0 ? s->rank : (int)P.n_meas;
+    if (meas > dsb::kMaxRegMeas || P.n_walkers >= (int64_t(1) << 31)) return 0;
+    if (const char *env = getenv("DISIMPY_B200_RESORT")) return std::max<int64_t>(0, atoll(env));
+    const dsb::MeshDev &m = s->mesh->dev;
+    const int64_t cells = int64_t(m.len_xs - 1) * (m.len_ys - 1) * (m.len_zs - 1);
+    if (P.n_walkers < DSB_RESORT_MIN_WALKERS || cells < 4096) return 0;
+    if (s->mesh->data_bytes + s->mesh->grid_bytes < DSB_RESORT_MIN_MESH_BYTES) return 0;
+    const double edge = std::max(m.vox[0], std::max(m.vox[1], m.vox[2]));   // the slabs are cut across this one
+    const double steps = 3.0 * (DSB_RESORT_DRIFT * edge / P.step_l) * (DSB_RESORT_DRIFT * edge / P.step_l);
+    return (int64_t)std::min(1e9, std::max(256.0, steps));   // (a NaN lands on 256)
+}
+
+// walkers of the handle into cell order (d_order), on stream st
+static int sort_walkers(dsb_sim *s, cudaStream_t st)
+{
+    const int64_t N = s->prm.n_walkers;
+    const dsb::MeshDev &m = s->mesh->dev;
+    if (!s->d_order) {
+        const int len[3] = {m.len_xs - 1, m.len_ys - 1, m.len_zs - 1};
+        for (int a = 0; a < 3; ++a) {
+            s->bins.n[a] = std::max(1, std::min(len[a], 128));
+            s->bins.inv_vox[a] = m.inv_vox[a];
+            s->bins.axis[a] = a;
+        }
+        // consecutive blocks share a slab across the longest edge of the voxel
+        std::stable_sort(s->bins.axis, s->bins.axis + 3, [&](int a, int b) { return m.vox[a] > m.vox[b]; });
+        DSB_CUDA(cache_malloc(&s->d_order, sizeof(int) * N));
+        DSB_CUDA(cache_malloc(&s->d_key, sizeof(int) * N));
+        DSB_CUDA(cache_malloc(&s->d_bins, sizeof(int) * s->bins.n[0] * s->bins.n[1] * s->bins.n[2]));
+    }
+    const int n_bins = s->bins.n[0] * s->bins.n[1] * s->bins.n[2];
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    DSB_CUDA(cudaMemsetAsync(s->d_bins, 0, sizeof(int) * n_bins, st));
+    dsb::cell_order_count<<<blocks, 256, 0, st>>>(s->d_pos, N, s->bins, s->d_key, s->d_bins);
+    dsb::cell_order_scan<<<1, 1024, 0, st>>>(s->d_bins, n_bins);
+    dsb::cell_order_scatter<<<blocks, 256, 0, st>>>(s->d_key, N, s->d_bins, s->d_order);
+    DSB_CUDA(cudaGetLastError());
+    s->n_launches += 3;
+    return DSB_OK;
+}
+
+// one launch of the walk kernel: walkers [w0, w1) over time steps [t0, t1); `sorted`: all walkers
+// of the handle, assigned to threads in cell order (the sort is part of the timed launch)
+static int launch_walk_range(dsb_sim *s, cudaStream_t st, int64_t w0, int64_t w1, int64_t t0, int64_t t1, bool sorted = false)
 {
     const dsb_params &P = s->prm;
     dsb::KParams kp{};
@@ -1353,7 +1431,8 @@ static int launch_walk_range(dsb_sim *s, cudaStream_t st, int64_t w0, int64_t w1
     kp.n_t = (int)P.n_t;
     kp.t0 = (int)t0;
     kp.t1 = (int)t1;
-    kp.finalize = t1 == P.n_t && s->rank == 0;  // low-rank protocols are reduced by lowrank_signal_kernel
+    kp.finalize = t1 == P.n_t && s->rank == 0 && !sorted;  // low-rank protocols are reduced by lowrank_signal_kernel
+    if (t1 == P.n_t) s->signal_from_phases = sorted && s->rank == 0;
     kp.max_iter = (int)std::min<int64_t>(P.max_iter, 0x7fffffff);
     kp.step_l = P.step_l;
     kp.gamma_dt = P.dt * 267.513e6;  // dt * GAMMA (gradients.py:13), one rounding like the reference
@@ -1376,6 +1455,15 @@ static int launch_walk_range(dsb_sim *s, cudaStream_t st, int64_t w0, int64_t w1
     DSB_CUDA(cudaEventCreate(&e0));
     DSB_CUDA(cudaEventCreate(&e1));
     DSB_CUDA(cudaEventRecord(e0, st));
+    if (sorted) {
+        int rc = sort_walkers(s, st);
+        if (rc) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            return rc;
+        }
+        kp.order = s->d_order;
+    }
     switch (P.substrate) {
     case DSB_FREE: launch_walk<0>(kp, grid, st); break;
     case DSB_SPHERE: launch_walk<1>(kp, grid, st); break;
@@ -1406,6 +1494,22 @@ static int launch_signal_reduction(dsb_sim *s)
         dsb::lowrank_signal_kernel<<<s->grid, dsb::kBlock, 0, s->stream>>>(kp, s->d_u, s->rank, (int)s->prm.n_meas);
         DSB_CUDA(cudaGetLastError());
         s->n_launches += 1;
+    } else if (s->signal_from_phases) {
+        dsb::KParams kp{};
+        kp.n_walkers = s->prm.n_walkers;
+        kp.n_blocks_total = s->grid;
+        kp.n_meas = (int)s->prm.n_meas;
+        kp.phases = s->d_phases;
+        kp.iter_exc = s->d_exc;
+        kp.partials = s->d_partials;
+        switch (kp.n_meas) {
+        case 1: dsb::phases_signal_kernel<1><<<s->grid, dsb::kBlock, 0, s->stream>>>(kp); break;
+        case 2: dsb::phases_signal_kernel<2><<<s->grid, dsb::kBlock, 0, s->stream>>>(kp); break;
+        case 3: dsb::phases_signal_kernel<3><<<s->grid, dsb::kBlock, 0, s->stream>>>(kp); break;
+        default: dsb::phases_signal_kernel<4><<<s->grid, dsb::kBlock, 0, s->stream>>>(kp); break;
+        }
+        DSB_CUDA(cudaGetLastError());
+        s->n_launches += 1;
     }
     dsb::reduce_partials_kernel<<<(unsigned)(s->prm.n_meas + 1), 256, 0, s->stream>>>(s->d_partials, s->grid, s->d_signal);
     DSB_CUDA(cudaGetLastError());
@@ -1424,7 +1528,14 @@ int dsb_run(dsb_sim *s, int64_t t0, int64_t t1)
     if (t0 != s->t_cur || t1 <= t0 || t1 > s->prm.n_t) return fail(DSB_EINVAL, "bad step range");
     Range nvtx("dsb_run: walk (+ signal reduction)");
     DSB_CUDA(cudaSetDevice(s->prm.device));
-    int rc = launch_walk_range(s, s->stream, 0, s->prm.n_walkers, t0, t1);
+    int rc = DSB_OK;
+    const int64_t resort = resort_interval(s);
+    if (resort > 0 && t1 - t0 >= std::min<int64_t>(resort, 64)) {   // (short calls -- trajectories, a few steps -- are not worth a sort)
+        for (int64_t a = t0; a < t1 && !rc; a += resort)
+            rc = launch_walk_range(s, s->stream, 0, s->prm.n_walkers, a, std::min<int64_t>(a + resort, t1), true);
+    } else {
+        rc = launch_walk_range(s, s->stream, 0, s->prm.n_walkers, t0, t1);
+    }
     if (rc) return rc;
     if (t1 == s->prm.n_t) {
         rc = launch_signal_reduction(s);

@@ -96,6 +96,7 @@ struct KParams {
     double *phases;             // (n_meas, n_walkers)
     unsigned char *iter_exc;    // (n_walkers,)
     double *partials;           // (n_meas + 1, n_blocks_total)
+    const int *order;           // mesh walk only, may be null: thread j of the launch advances walker order[j] (cell order)
     MeshDev mesh;
 };
 
@@ -893,8 +894,12 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
     if (threadIdx.x < 16) s_tab[threadIdx.x] = __longlong_as_double((long long)c_sincos_tab[threadIdx.x]);
     __syncthreads();
 
-    const long long w = p.w_begin + (long long)blockIdx.x * kBlock + threadIdx.x;
+    long long w = p.w_begin + (long long)blockIdx.x * kBlock + threadIdx.x;
     const bool active = w < p.w_end;
+    if constexpr (SUB == 4 && MR > 0) {
+        // walkers in cell order (cell_order_* kernels below): the lanes of a warp search the same few lists
+        if (p.order != nullptr && active) w = __ldg(p.order + w);
+    }
     const long long N = p.n_walkers;
     Vec3 pos = {0.0, 0.0, 0.0};
     Rng rng = {1ull, 1ull};
@@ -1196,6 +1201,93 @@ __global__ void __launch_bounds__(kBlock, SUB == 4 ? DSB_MESH_MIN_BLOCKS : (MR =
 // different timings give rank <= 3k), the walk carries the r phases psi of the rows of V (in
 // registers for r <= kMaxRegMeas, through the many-measurement kernels above that) and the
 // n_meas real phases are phi[m, i] = sum_k U[m, k] psi[k, i], formed once at the end.
+
+// per-block partial sums of cos(phase) from the phase array, for runs whose last launch did not
+// advance the walkers in index order (same partials, same summation tree as walk_kernel's own)
+template <int MR>
+__global__ void __launch_bounds__(kBlock) phases_signal_kernel(const KParams p)
+{
+    const long long w = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const bool active = w < p.n_walkers;
+    double ph[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) ph[m] = active ? p.phases[(long long)m * p.n_walkers + w] : 0.0;
+    block_signal(p, active && p.iter_exc[w] == 0, [&](int m) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < MR; ++k)
+            if (k == m) v = ph[k];
+        return v;
+    });
+}
+
+// ---------------------------------------------------------------- walkers in cell order
+//
+// A mesh walk with the walkers in index order has the ~600 resident blocks spread over the whole
+// mesh, and a mesh larger than the L2 is then read from HBM over and over.  A counting sort of the
+// walkers by the grid cell they start in (cell_order_count -> cell_order_scan -> cell_order_scatter)
+// puts the walkers of consecutive blocks into one slab of the mesh (dsb_api.cu, resort_interval,
+// has the measurements and says when the sort is repeated).  Only the assignment of walkers to
+// threads changes: every walker runs its own stream from its own state and writes its own slots,
+// so results do not depend on the order (the order inside a cell is whatever the atomics give).
+
+struct CellBins {
+    int n[3];          // bins per axis (the reference grid's cells, at most 128 per axis)
+    double inv_vox[3];
+    int axis[3];       // sort order: axis[0] (the longest edge of the voxel) varies slowest
+};
+
+__device__ __forceinline__ int cell_bin(const double *pos, long long i, const CellBins &b)
+{
+    int idx[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double f = pos[3 * i + a] * b.inv_vox[a];
+        f -= floor(f);                                   // periodic image; positions inside the voxel are unchanged
+        idx[a] = min(max((int)(f * b.n[a]), 0), b.n[a] - 1);   // (a NaN position converts to 0)
+    }
+    return (idx[b.axis[0]] * b.n[b.axis[1]] + idx[b.axis[1]]) * b.n[b.axis[2]] + idx[b.axis[2]];
+}
+
+__global__ void __launch_bounds__(256) cell_order_count(const double *pos, long long n, CellBins b, int *key, int *count)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = cell_bin(pos, i, b);
+    key[i] = k;
+    atomicAdd(count + k, 1);
+}
+
+// exclusive prefix sums of the bin counts, in place; one block (the array is a few MB at most)
+__global__ void __launch_bounds__(1024) cell_order_scan(int *count, int n_bins)
+{
+    __shared__ int s_sum[1024];
+    const int per = (n_bins + 1023) / 1024;
+    const int b = min(threadIdx.x * per, n_bins), e = min(b + per, n_bins);
+    int acc = 0;
+    for (int i = b; i < e; ++i) acc += count[i];
+    s_sum[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = (int)threadIdx.x >= o ? s_sum[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = s_sum[threadIdx.x] - acc;
+    for (int i = b; i < e; ++i) {
+        const int c = count[i];
+        count[i] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(256) cell_order_scatter(const int *key, long long n, int *cursor, int *order)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    order[atomicAdd(cursor + key[i], 1)] = (int)i;
+}
 
 // per-block partial sums of cos(phi) over unflagged walkers (same layout as block_signal writes)
 __global__ void __launch_bounds__(kBlock) lowrank_signal_kernel(const KParams p, const double *u, int rank, int n_real)

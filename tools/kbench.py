@@ -96,7 +96,7 @@ def main():
             sig, n_valid = walk.signal()
             ms, nl = walk.run_stats()
             best = ms if best is None else min(best, ms)
-        print("%-12s n=%d T=%d M=%d  kernel %.2f ms  %.3e walker-steps/s  signal[0]=%.6f valid=%d"
+        print("%-12s n=%d T=%d M=%d  kernel %.2f ms  %.3e walker-steps/s  signal[0]=%.10f valid=%d"
               % (case, n, g.shape[1], g.shape[0], best, n * g.shape[1] / (best * 1e-3), sig[0], n_valid),
               flush=True)
         walk.close()
