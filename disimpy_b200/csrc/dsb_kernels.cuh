@@ -587,7 +587,8 @@ __device__ __forceinline__ void mesh_closest_hit(const MeshDev &g, MeshScratch &
         if constexpr (MAXC == kMaxCellsShortStep) {
             // (All eight slots, unrolled and predicated, although a lane has entries in one to three of them --
             // 257 instructions per warp-step at 5 active lanes.  A loop over the lane's non-empty slots only, their
-            // ranges parked in shared memory, was measured: -21 %, profiles/r02_n_kbench_range_loop.txt.)
+            // ranges parked in shared memory, was measured: -21 %, profiles/r02_n_kbench_range_loop.txt; eight votes and a
+            // warp-uniform skip of the slots in which no lane has a list: -1.7 %, profiles/r02_al_kbench_slot_vote.txt.)
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 add_range(c, ((c >> 2) & wrap_x) | ((((c >> 1) & 1) & wrap_y) << 1) | (((c & 1) & wrap_z) << 2));
