@@ -1807,6 +1807,26 @@ int dsb_selftest_sqrt(int32_t device, uint64_t seed, int32_t exp_lo, int32_t exp
     return DSB_OK;
 }
 
+int dsb_selftest_device_function(int32_t device, int32_t op, int64_t n, const double *in, double *out)
+{
+    if (op < 0 || op >= dsb::kUnitOps || n <= 0 || !in || !out) return fail(DSB_EINVAL, "bad arguments");
+    DSB_CUDA(cudaSetDevice(device));
+    const size_t bytes_in = sizeof(double) * (size_t)n * dsb::unit_n_in(op), bytes_out = sizeof(double) * (size_t)n * dsb::unit_n_out(op);
+    double *d_in = nullptr, *d_out = nullptr;
+    DSB_CUDA(cudaMalloc(&d_in, bytes_in));
+    cudaError_t e = cudaMalloc(&d_out, bytes_out);
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, in, bytes_in, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        dsb::device_function_kernel<<<(unsigned)((n + 127) / 128), 128>>>(op, n, d_in, d_out);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, bytes_out, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? DSB_ENOMEM : DSB_ECUDA, cudaGetErrorString(e));
+    return DSB_OK;
+}
+
 int dsb_protocol_rank(dsb_sim *s) { return s ? s->rank : 0; }
 
 int dsb_protocol_factor(const double *gradient, int64_t n_meas, int64_t n_t, int32_t max_rank, int32_t *rank, double *u,

@@ -1399,6 +1399,75 @@ __global__ void ellipsoid_consts_kernel(double a0, double a1, double a2, Ellipso
     }
 }
 
+// ---------------------------------------------------------------- device functions one at a time
+
+// The walk's device functions on rows of arguments, the way the reference's unit tests call its
+// `_cuda_*` functions through small test kernels (disimpy/tests/test_simulations.py:23-360);
+// layouts in include/disimpy_b200.h (dsb_selftest_device_function).
+constexpr int kUnitOps = 11;
+__host__ __device__ constexpr int unit_n_in(int op)
+{
+    constexpr int n[kUnitOps] = {6, 6, 3, 9, 12, 5, 7, 9, 15, 11, 11};
+    return n[op];
+}
+__host__ __device__ constexpr int unit_n_out(int op)
+{
+    constexpr int n[kUnitOps] = {1, 3, 3, 3, 3, 1, 1, 1, 1, 6, 3};
+    return n[op];
+}
+
+__global__ void __launch_bounds__(128) device_function_kernel(int op, long long n, const double *in, double *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *a = in + i * unit_n_in(op);
+    double *o = out + i * unit_n_out(op);
+    auto vec = [&](int k) { return Vec3{a[k], a[k + 1], a[k + 2]}; };
+    auto put = [&](int k, const Vec3 &v) { o[k] = v.x; o[k + 1] = v.y; o[k + 2] = v.z; };
+    auto tri = [&](int k) {   // corner and edges, as the upload stores a triangle
+        Tri t;
+        t.A = vec(k);
+        t.E1 = Vec3{sub_(a[k + 3], a[k]), sub_(a[k + 4], a[k + 1]), sub_(a[k + 5], a[k + 2])};
+        t.E2 = Vec3{sub_(a[k + 6], a[k]), sub_(a[k + 7], a[k + 1]), sub_(a[k + 8], a[k + 2])};
+        return t;
+    };
+    switch (op) {
+    case 0: o[0] = dot3(vec(0), vec(3)); break;
+    case 1: put(0, cross3(vec(0), vec(3))); break;
+    case 2: put(0, normalize3(vec(0))); break;
+    case 3: put(0, triangle_normal(tri(0))); break;
+    case 4: put(0, matvec3(a, vec(9))); break;
+    case 5: o[0] = line_circle(Vec3{0.0, a[0], a[1]}, Vec3{0.0, a[2], a[3]}, a[4]); break;
+    case 6: o[0] = line_sphere(vec(0), vec(3), a[6]); break;
+    case 7: {
+        EllipsoidConsts e;   // as ellipsoid_consts_kernel fills them
+        for (int k = 0; k < 3; ++k) {
+            e.ax[k] = a[6 + k];
+            e.ax_rc[k] = rcp_refined(e.ax[k]);
+            e.axsq[k] = mul_(e.ax[k], e.ax[k]);
+            e.ax_isq[k] = rcp_(e.axsq[k]);
+            e.axsq_rc[k] = rcp_refined(e.axsq[k]);
+        }
+        o[0] = line_ellipsoid(vec(0), vec(3), e);
+        break;
+    }
+    case 8: o[0] = ray_triangle(tri(0), vec(9), vec(12)); break;
+    case 9: {
+        Vec3 r0 = vec(0), s = vec(3);
+        reflect(r0, s, a[6], vec(7), a[10]);
+        put(0, r0);
+        put(3, s);
+        break;
+    }
+    default: {
+        Vec3 r0 = vec(0);
+        cross_membrane(r0, vec(3), a[6], vec(7), a[10]);
+        put(0, r0);
+        break;
+    }
+    }
+}
+
 // ---------------------------------------------------------------- self-test of sqrt_fast
 
 // sqrt_fast(x) against __dsqrt_rn(x), bit for bit, on pseudo-random arguments: thread i tests `per_thread`

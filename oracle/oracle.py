@@ -74,6 +74,26 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+UNIT_OPS = {"dot_product": (0, 6, 1), "cross_product": (1, 6, 3), "normalize_vector": (2, 3, 3),
+            "triangle_normal": (3, 9, 3), "mat_mul": (4, 12, 3), "line_circle_intersection": (5, 5, 1),
+            "line_sphere_intersection": (6, 7, 1), "line_ellipsoid_intersection": (7, 9, 1),
+            "ray_triangle_intersection_check": (8, 15, 1), "reflection": (9, 11, 6), "crossing": (10, 11, 3)}
+
+
+def unit(name, args):
+    """One of the reference's device functions (disimpy/simulations.py:23-343, `_cuda_<name>`) on
+    the rows of `args` (layout: oracle_unit in disimpy_oracle.c)."""
+    op, n_in, n_out = UNIT_OPS[name]
+    a = np.ascontiguousarray(np.atleast_2d(np.asarray(args, dtype=np.float64)))
+    assert a.shape[1] == n_in, (name, a.shape)
+    out = np.zeros((a.shape[0], n_out))
+    L = lib()
+    L.oracle_unit.restype = ctypes.c_int
+    rc = L.oracle_unit(ctypes.c_int(op), ctypes.c_int64(a.shape[0]), _ptr(a), _ptr(out))
+    assert rc == 0
+    return out
+
+
 def rng_states(seed, n, subsequence_start=0):
     """(n, 2) uint64 xoroshiro128+ states; numba/cuda/random.py:225-241."""
     out = np.zeros((n, 2), dtype=np.uint64)

@@ -85,3 +85,97 @@ def product_substrate(name, g):
     return substrates.mesh(g["mesh_vertices_in"], g["mesh_faces_in"], bool(g["periodic"]),
                            padding=g["padding"], init_pos=ip if ip.ndim == 2 else str(ip),
                            n_sv=g["n_sv"], quiet=True, perm_prob=0 if pp == 0 else pp)
+
+
+def check_device_function_known_answers(unit):
+    """The reference's unit tests of its device functions (disimpy/tests/test_simulations.py:23-109,
+    142-360) with `unit(name, rows_of_arguments) -> rows_of_results` standing in for the test kernels:
+    dot / cross / normalize / triangle normal / mat_mul against NumPy on 100 random cases, and the
+    known answers for the intersection checks, the reflection and the crossing (7 decimals, like
+    npt.assert_almost_equal there)."""
+    import numpy.testing as npt
+    rs = np.random.RandomState(123)
+    a, b = rs.random_sample((100, 3)) - 0.5, rs.random_sample((100, 3)) - 0.5
+    npt.assert_almost_equal(unit("dot_product", np.hstack([a, b]))[:, 0], np.einsum("ij,ij->i", a, b))
+    npt.assert_almost_equal(unit("cross_product", np.hstack([a, b])), np.cross(a, b))
+    npt.assert_almost_equal(unit("normalize_vector", a), a / np.linalg.norm(a, axis=1)[:, None])
+    tri = rs.random_sample((100, 3, 3)) - 0.5
+    n = np.cross(tri[:, 0] - tri[:, 1], tri[:, 0] - tri[:, 2])
+    npt.assert_almost_equal(unit("triangle_normal", tri.reshape(100, 9)), n / np.linalg.norm(n, axis=1)[:, None])
+    R = rs.random_sample((100, 3, 3)) - 0.5
+    npt.assert_almost_equal(unit("mat_mul", np.hstack([R.reshape(100, 9), a])), np.einsum("nij,nj->ni", R, a))
+    s = np.array([1.0, 1.0, 0.0]) / np.linalg.norm([1.0, 1.0, 0.0])
+    npt.assert_almost_equal(unit("line_circle_intersection", [[-0.1, -0.1, s[0], s[1], 1.0]])[0, 0], 1.1414213562373097)
+    npt.assert_almost_equal(unit("line_sphere_intersection", [[-0.1, -0.1, 0.0, *s, 1.0]])[0, 0], 1.1414213562373097)
+    npt.assert_almost_equal(unit("line_ellipsoid_intersection", [[-0.1, -0.1, 0.0, *s, 1.0, 1.0, 1.0]])[0, 0],
+                            1.1414213562373097)
+    triangle = [2.0, 0, 0, 0, 2.0, 0, 0.0, 0, 0]
+    r0s = [[0.1, 0.1, 1.0]] * 4 + [[10.0, 10.0, 0.0]]
+    steps = [[0, 0, -1.0], [0, 0, 1.0], [0, 0, -0.1], [1.0, 1.0, 0], [0, 0, 1.0]]
+    ds = unit("ray_triangle_intersection_check", [triangle + r + st for r, st in zip(r0s, steps)])
+    npt.assert_almost_equal(ds, np.array([[1, -1, 10, np.nan, np.nan]]).T)
+    normal = np.array([0.0, 1.0, 1.0]) / np.linalg.norm([0.0, 1.0, 1.0])
+    # (the reference's kernel flips its `normal` array in place so that it points against the step, and the
+    # second expectation there is written with the array the first call left behind: -normal)
+    for eps in (0.0, 0.5):
+        for nrm in (normal, -normal):
+            out = unit("reflection", [[0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.5, *nrm, eps]])[0]
+            npt.assert_almost_equal(out[3:], [0.0, -1.0, 0.0])
+            npt.assert_almost_equal(out[:3], np.array([0.0, 0.0, 0.5]) - normal * eps)
+    # a bounce off the triangle (0,0,0) (1,0,0) (0,1,0) from above: hit at d = 0.5, back up, eps above the plane
+    tri = [0.0, 0, 0, 1.0, 0, 0, 0, 1.0, 0]
+    r0, step, eps = [0.0, 0.0, 0.5], [0.0, 0.0, -1.0], 1e-10
+    d = unit("ray_triangle_intersection_check", [tri + r0 + step])[0, 0]
+    assert 0 < d < 1.0
+    nrm = unit("triangle_normal", [tri])[0]
+    out = unit("reflection", [r0 + step + [d] + list(nrm) + [eps]])[0]
+    npt.assert_almost_equal(out[3:], [0.0, 0.0, 1.0])
+    npt.assert_almost_equal(out[:3], [0.0, 0.0, eps])
+    assert out[2] == eps
+    # through the triangle (0,0,1) (1,0,1) (0,1,1) from below: eps beyond the membrane
+    tri = [0.0, 0, 1.0, 1.0, 0, 1.0, 0, 1.0, 1.0]
+    r0, step = [0.0, 0.0, 0.0], [0.0, 0.0, 1.0]
+    d = unit("ray_triangle_intersection_check", [tri + r0 + step])[0, 0]
+    assert 0 < d < 2
+    nrm = unit("triangle_normal", [tri])[0]
+    out = unit("crossing", [r0 + step + [d] + list(nrm) + [eps]])[0]
+    npt.assert_almost_equal(out, [0.0, 0.0, 1 + eps], decimal=12)
+
+
+def device_function_random_rows(name, n, seed=5):
+    """Random argument rows for `name` (collisions that really happen where the function expects
+    one), for bit-for-bit comparisons between two implementations."""
+    rs = np.random.RandomState(seed)
+    u = lambda *shape: rs.random_sample(shape) - 0.5
+    unit_vec = lambda: (lambda v: v / np.linalg.norm(v, axis=1)[:, None])(rs.normal(size=(n, 3)))
+    if name in ("dot_product", "cross_product"):
+        return np.hstack([u(n, 3), u(n, 3)])
+    if name == "normalize_vector":    # + zero, overflowing and underflowing squared lengths
+        rows = u(n, 3) * 10.0 ** rs.randint(-8, 3, size=(n, 1))
+        rows[:6] = [[0, 0, 0], [1e200, 1e200, 0], [1e-200, 0, 1e-200], [0, -0.0, 3e-160], [1e154, 1e154, 1e154], [5e-324, 0, 0]]
+        return rows
+    if name == "triangle_normal":     # + triangles without area (NaN normals)
+        rows = u(n, 9) * 1e-5
+        rows[0, 3:6] = rows[0, 0:3]
+        rows[1, 6:9] = rows[1, 3:6]
+        rows[2] = 0.0
+        return rows
+    if name == "mat_mul":
+        return np.hstack([u(n, 9), u(n, 3) * 1e-5])
+    if name == "line_circle_intersection":
+        sv = unit_vec()
+        return np.hstack([u(n, 2) * 1e-5, sv[:, 1:], np.full((n, 1), 1e-5)])
+    if name == "line_sphere_intersection":   # + starting points outside the sphere (negative discriminants: NaN)
+        rows = np.hstack([u(n, 3) * 1e-5, unit_vec(), np.full((n, 1), 1e-5)])
+        rows[:50, :3] *= 4.0
+        return rows
+    if name == "line_ellipsoid_intersection":
+        return np.hstack([u(n, 3) * 1e-6, unit_vec(), np.tile([1e-5, 5e-6, 2.5e-6], (n, 1))])
+    if name == "ray_triangle_intersection_check":   # + rays in the triangle's plane (zero determinant)
+        rows = np.hstack([u(n, 9) * 1e-5, u(n, 3) * 1e-5, unit_vec()])
+        rows[:20, 2:9:3] = 0.0
+        rows[:20, 14] = 0.0
+        return rows
+    if name in ("reflection", "crossing"):
+        return np.hstack([u(n, 3) * 1e-5, unit_vec(), rs.random_sample((n, 1)) * 1e-6, unit_vec(), np.full((n, 1), 1e-13)])
+    raise KeyError(name)

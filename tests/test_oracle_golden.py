@@ -89,3 +89,10 @@ def test_oracle_shards_compose():
                    walker_offset=200)
     assert np.array_equal(np.vstack([a["positions"], b["positions"]]), full["positions"])
     assert np.array_equal(np.hstack([a["phases"], b["phases"]]), full["phases"])
+
+
+def test_device_function_known_answers():
+    """the oracle's restatements of the reference's device functions against the known
+    answers of the reference's own unit tests (disimpy/tests/test_simulations.py:23-360)."""
+    from conftest import check_device_function_known_answers
+    check_device_function_known_answers(O.unit)
