@@ -62,6 +62,31 @@ def test_free_diffusion(tmp_path):  # :469-500
     npt.assert_almost_equal(np.mean(tr[-1], axis=0), 0, 5)
 
 
+def test_random_step_like_reference():  # :110-139 (test__cuda_random_step)
+    """One time step of free diffusion from the origin = one `_cuda_random_step` per walker: same
+    seed -> same steps, another seed -> every component differs, zero mean, unit length, and --
+    beyond the reference's test -- the oracle's steps bit for bit."""
+    from scipy.stats import normaltest
+    from disimpy_b200 import simulations, substrates
+    from oracle import oracle as O
+    N, dt = int(1e5), 1e-3
+    g = np.zeros((1, 1, 3))
+    g[0, 0, 0] = 0.01
+    step_l = np.sqrt(6 * D * dt)
+    steps = np.zeros((3, N, 3))
+    for i, seed in enumerate([1, 1, 12]):
+        _, pos = simulations.simulation(N, D, g, dt, substrates.free(), seed=seed, final_pos=True, quiet=True)
+        steps[i] = pos / step_l
+    npt.assert_equal(steps[0], steps[1])
+    assert np.all(steps[0] != steps[2])
+    npt.assert_almost_equal(np.mean(np.sum(steps[1::], axis=1) / N), 0, 3)
+    _, p = normaltest(steps[1::].ravel())
+    npt.assert_almost_equal(p, 0)
+    npt.assert_almost_equal(np.linalg.norm(steps, axis=2), np.ones((3, N)))
+    ref = O.simulation(N, D, g, dt, substrates.free(), seed=12, n_threads=8)
+    assert np.array_equal(steps[2] * step_l, ref["positions"])
+
+
 @pytest.mark.parametrize("shape", ["sphere", "cylinder"])
 def test_signal_against_misst(shape):  # :521-566, :602-654
     from disimpy_b200 import simulations, substrates
