@@ -80,22 +80,41 @@ class _HostSampler:
             pass
 
 
-def _fill_circle(n, radius, seed):
+_SEED = None
+
+
+def _set_seed(seed):
+    """simulations.py:346-350: the seed of the host samplers below when they are called without
+    one, as the reference's are (there it seeds Numba's CPU generator)."""
+    global _SEED
+    _SEED = int(seed)
+
+
+def _stream_seed(seed):
+    """The MT19937 stream a sampler call draws from: the given seed (what simulation() passes), else
+    the one of _set_seed, else a fresh one from NumPy's global generator (the reference's samplers
+    then continue whatever state Numba's generator is in; here every call starts its stream)."""
+    if seed is not None:
+        return seed
+    return _SEED if _SEED is not None else int(np.random.randint(0, 2 ** 32, dtype=np.uint64))
+
+
+def _fill_circle(n, radius, seed=None):
     """n points uniform in a disc (simulations.py:353-366) from the MT19937 stream of ``seed``."""
-    return _host_fill(0, n, seed, radius, 2)
+    return _host_fill(0, n, _stream_seed(seed), radius, 2)
 
 
-def _fill_sphere(n, radius, seed):
+def _fill_sphere(n, radius, seed=None):
     """n points uniform in a ball (simulations.py:369-382)."""
-    return _host_fill(1, n, seed, radius, 3)
+    return _host_fill(1, n, _stream_seed(seed), radius, 3)
 
 
-def _fill_ellipsoid(n, semiaxes, seed):
+def _fill_ellipsoid(n, semiaxes, seed=None):
     """n points uniform in an axis-aligned ellipsoid (simulations.py:385-399)."""
-    return _host_fill(2, n, seed, semiaxes, 3)
+    return _host_fill(2, n, _stream_seed(seed), semiaxes, 3)
 
 
-def _initial_positions_cylinder(n_walkers, radius, R, seed):
+def _initial_positions_cylinder(n_walkers, radius, R, seed=None):
     """Points in the cross-section of a cylinder, rotated to the lab frame by R
     (simulations.py:402-409)."""
     positions = np.zeros((n_walkers, 3))
@@ -103,7 +122,7 @@ def _initial_positions_cylinder(n_walkers, radius, R, seed):
     return np.matmul(R, positions.T).T
 
 
-def _initial_positions_ellipsoid(n_walkers, semiaxes, R, seed):
+def _initial_positions_ellipsoid(n_walkers, semiaxes, R, seed=None):
     """Points in an ellipsoid, rotated to the lab frame by R (simulations.py:412-418)."""
     return np.matmul(R, _fill_ellipsoid(n_walkers, semiaxes, seed).T).T
 

@@ -169,6 +169,32 @@ def _mesh_space_subdivision(vertices, faces, voxel_size, n_sv):
     return xs, ys, zs, triangle_indices.astype(int), subvoxel_indices.astype(int)
 
 
+def _cross_product(a, b):
+    """substrates.py:272-280 (the subdivision's own copies of these helpers live in csrc/dsb_subdivide.cpp)."""
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]])
+
+
+def _dot_product(a, b):
+    """substrates.py:283-287."""
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+
+
+def _triangle_aabb(triangle):
+    """Corners of the triangle's bounding box closest to and furthest from the origin, (2, 3);
+    substrates.py:422-441."""
+    t = np.asarray(triangle, dtype=float)
+    return np.vstack((t.min(axis=0), t.max(axis=0)))
+
+
+def _box_subvoxel_overlap(box, xs, ys, zs):
+    """Lowest and highest (exclusive) subvoxel index the box overlaps along each axis, (3, 2) int32;
+    substrates.py:444-464."""
+    subvoxels = np.zeros((3, 2), dtype=np.int32)
+    for i, a in enumerate([xs, ys, zs]):
+        subvoxels[i] = _interval_sv_overlap(a, box[0, i], box[1, i])
+    return subvoxels
+
+
 def _triangle_box_overlap(triangle, box):
     """True when the triangle (3, 3) overlaps the box (2, 3); substrates.py:290-368."""
     return bool(_lib.lib().dsb_triangle_box_overlap(_lib.ptr(_lib.f64(triangle)),

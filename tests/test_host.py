@@ -124,7 +124,7 @@ def test_mesh_validation_and_layout():
 
 
 def test_reference_unit_known_answers():
-    """tests/test_substrates.py:293-363 of the reference."""
+    """tests/test_substrates.py:273-363 and :450-480 of the reference."""
     from disimpy_b200 import substrates
     tri = np.array([[0.5, 0.7, 0.3], [0.9, 0.5, 0.2], [0.6, 0.9, 0.8]])
     assert not substrates._triangle_box_overlap(tri, np.array([[0.1, 0.3, 0.1], [0.4, 0.7, 0.5]]))
@@ -140,6 +140,23 @@ def test_reference_unit_known_answers():
     assert substrates._interval_sv_overlap(xs, 9.5, 1.5) == (1, 10)
     assert substrates._interval_sv_overlap(xs, -1.1, 0.5) == (0, 1)
     assert substrates._interval_sv_overlap(xs, 9.5, 11.5) == (9, 10)
+    # :273-290 (cross / dot against NumPy), :347-365 (bounding box, subvoxel range), :450-480 (box -> mesh)
+    rs = np.random.RandomState(123)
+    for _ in range(100):
+        a, b = rs.random_sample(3) - 0.5, rs.random_sample(3) - 0.5
+        assert np.allclose(substrates._cross_product(a, b), np.cross(a, b), atol=1e-7)
+        assert np.isclose(substrates._dot_product(a, b), np.dot(a, b), atol=1e-7)
+    tri = np.array([[0.5, 0.7, 0.3], [0.9, 0.5, 0.2], [0.6, 0.9, 0.8]])
+    assert np.array_equal(substrates._triangle_aabb(tri), np.vstack((tri.min(axis=0), tri.max(axis=0))))
+    box = np.array([[2.5, 5.0, 2.2], [9.2, 9.5, 20]])
+    assert np.array_equal(substrates._box_subvoxel_overlap(box, np.arange(6), np.arange(11), np.arange(21)),
+                          np.array([[2, 5], [5, 10], [2, 20]]))
+    vertices = np.array([[2.5, 5.0, 2.2], [9.2, 5.0, 2.2], [9.2, 9.5, 2.2], [9.2, 9.5, 20.0], [2.5, 9.5, 20.0],
+                         [2.5, 5.0, 20.0], [2.5, 9.5, 2.2], [9.2, 5.0, 20.0]])
+    faces = np.array([[0, 1, 2], [0, 6, 2], [5, 7, 3], [5, 4, 3], [1, 2, 3], [1, 7, 3], [0, 6, 4], [0, 5, 4],
+                      [0, 1, 7], [0, 5, 7], [6, 2, 3], [6, 4, 3]])
+    v, f = substrates._aabb_to_mesh(box[0], box[1])
+    assert np.array_equal(v, vertices) and np.array_equal(f, faces)
 
 
 def test_mesh_subdivision_reference_golden():
@@ -252,6 +269,48 @@ def test_initial_positions_match_reference_stream():
     assert np.array_equal(c, O.initial_positions(csub, 2000, 5)[:, 1:3])
     with pytest.raises(ValueError):
         simulations._fill_sphere(10, 1e-6, 2 ** 32)
+
+
+def test_host_samplers_like_reference():
+    """The reference's tests of its host samplers (disimpy/tests/test_simulations.py:363-425), same
+    sizes, same assertions."""
+    import numpy.testing as npt
+    from scipy.stats import kstest
+    from disimpy_b200 import simulations, utils
+    radius, N = 5e-6, int(1e5)
+    for fill in (simulations._fill_circle, simulations._fill_sphere):
+        points = fill(N, radius)
+        assert np.max(np.linalg.norm(points, axis=1)) < radius
+        npt.assert_almost_equal(np.mean(points, axis=0), 0)
+        _, p = kstest((points.ravel() + radius) / radius, "uniform")
+        npt.assert_almost_equal(p, 0)
+    a, b, c = 10e-6, 2e-6, 5e-6
+    points = simulations._fill_ellipsoid(N, np.array([a, b, c]))
+    assert np.all(np.max(points, axis=0) < [a, b, c]) and np.all(np.min(points, axis=0) > [-a, -b, -c])
+    npt.assert_almost_equal(np.mean(points, axis=0), 0)
+    for i, r in enumerate([a, b, c]):
+        _, p = kstest((points[:, i].ravel() + r) / r, "uniform")
+        npt.assert_almost_equal(p, 0)
+    N, r = int(1e3), 5e-6
+    R = utils.vec2vec_rotmat(np.array([1.0, 0, 0]), np.array([0, 1.0, 0]))
+    R_inv = np.linalg.inv(R)
+    pos = simulations._initial_positions_cylinder(N, r, R)
+    npt.assert_almost_equal(pos[:, 1], np.zeros(N))
+    npt.assert_almost_equal(np.matmul(R_inv, pos.T)[0], np.zeros(N))
+    pos = simulations._initial_positions_ellipsoid(N, np.array([r, r, 1e-22]), R)
+    npt.assert_almost_equal(pos[:, 2], np.zeros(N))
+    npt.assert_almost_equal(np.matmul(R_inv, pos.T)[2], np.zeros(N))
+    # _set_seed + a call without a seed == the explicit seed == RandomState(seed)'s rejection stream
+    simulations._set_seed(77)
+    pts = simulations._fill_sphere(1000, r)
+    assert np.array_equal(pts, simulations._fill_sphere(1000, r, 77))
+    seq, manual = np.random.RandomState(77), []
+    while len(manual) < 20:
+        q = (seq.random_sample(3) - 0.5) * 2 * r
+        if np.linalg.norm(q) < r:
+            manual.append(q)
+    assert np.array_equal(pts[:20], np.array(manual))
+    simulations._SEED = None
 
 
 def test_simulation_argument_validation():
