@@ -30,6 +30,7 @@ import numpy as np
 
 from . import _lib, substrates, utils
 from .gradients import GAMMA  # noqa: F401  (same module-level name as the reference)
+from .substrates import _aabb_to_mesh  # noqa: F401  (simulations.py:582-613 is a second copy of it there)
 
 
 # ----------------------------------------------------------------------------------------
