@@ -70,7 +70,7 @@ EXPORTS = [
     "dsb_rewind", "dsb_set_positions_part", "dsb_run_part", "dsb_finish", "dsb_release_cache",
     "dsb_set_rng_states", "dsb_fill_mesh_sim", "dsb_protocol_rank", "dsb_protocol_factor", "dsb_set_rng_part", "dsb_host_sampler_create", "dsb_host_sampler_next", "dsb_host_sampler_destroy",
     "dsb_fill_shard_begin", "dsb_fill_shard_round", "dsb_fill_shard_end",
-    "dsb_copy_signal_dev", "dsb_simulate_multi", "dsb_fill_mesh_multi", "dsb_selftest_sqrt", "dsb_measure_l2_peak", "dsb_selftest_device_function",
+    "dsb_copy_signal_dev", "dsb_simulate_multi", "dsb_fill_mesh_multi", "dsb_selftest_sqrt", "dsb_measure_l2_peak", "dsb_selftest_device_function", "dsb_format_traj_line",
     "dsb_nccl_unique_id", "dsb_nccl_init", "dsb_allreduce_signal", "dsb_allreduce_zeros", "dsb_nccl_destroy",
 ]
 
@@ -151,6 +151,7 @@ def lib():
                                         c_int64_p, c_double_p]
         L.dsb_selftest_device_function.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p,
                                                    ctypes.c_void_p]
+        L.dsb_format_traj_line.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, c_int64_p]
         L.dsb_nccl_unique_id.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
         L.dsb_nccl_init.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                     ctypes.POINTER(ctypes.c_void_p)]

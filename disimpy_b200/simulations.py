@@ -167,11 +167,21 @@ def add_noise_to_data(data, sigma, seed=None):
     return np.abs(data + real + 1j * imag)
 
 
+def _traj_line(positions):
+    """The text of one time point as the reference writes it (simulations.py:1043-1048): str(v) + " "
+    for every value of positions.ravel(), then a newline -- formatted natively (dsb_format_traj_line:
+    the same characters, ~100 times faster than a str() per value)."""
+    v = _lib.f64(positions).ravel()
+    buf = np.empty(26 * v.size + 1, dtype=np.uint8)
+    n = ctypes.c_int64(0)
+    _lib.check(_lib.lib().dsb_format_traj_line(_lib.ptr(v), v.size, _lib.ptr(buf), buf.size, ctypes.byref(n)), "dsb_format_traj_line")
+    return memoryview(buf[:n.value])
+
+
 def _write_traj(traj, mode, positions):
     """One line per time point: x y z of walker 1, walker 2, ... (simulations.py:1043-1048)."""
-    with open(traj, mode) as f:
-        f.write("".join(str(v) + " " for v in positions.ravel()))
-        f.write("\n")
+    with open(traj, mode + "b") as f:
+        f.write(_traj_line(positions))
 
 
 def _device_count():

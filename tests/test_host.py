@@ -313,6 +313,25 @@ def test_host_samplers_like_reference():
     simulations._SEED = None
 
 
+def test_traj_line_equals_python_str():
+    """simulations.py:1043-1048 writes str(value) + " " per value; the native formatter must produce the
+    same characters for every double (shortest round-trip digits, Python's layout), on its serial
+    and its threaded path."""
+    from disimpy_b200 import simulations
+    rs = np.random.RandomState(0)
+    v = np.concatenate([rs.normal(size=200000) * 10.0 ** rs.randint(-320, 300, size=200000),
+                        rs.normal(size=100000) * 1e-5, rs.randint(-1000, 1000, size=1000).astype(float),
+                        np.arange(-20, 20) * 0.1, 10.0 ** np.arange(-25, 25), -(10.0 ** np.arange(-25, 25)) * 1.5,
+                        [0.0, -0.0, np.nan, np.inf, -np.inf, 1e16, 1e15, 9999999999999998.0, 1e-4, 9.9e-5, 5e-324,
+                         -5e-324, 1.7976931348623157e308, -1.7976931348623157e308, 123456789012345680.0,
+                         2.2250738585072014e-308, 0.1, 1 / 3, 2 / 3, 1e22, 1e23]])
+    for part in (v, v[:1000], v[-7:], v[:1], v[:0]):
+        want = ("".join(str(x) + " " for x in part) + "\n").encode()
+        assert bytes(simulations._traj_line(part)) == want
+    back = np.array(bytes(simulations._traj_line(v[:200000])).split(), dtype=float)
+    assert np.array_equal(back, v[:200000])       # and every value reads back to the same double
+
+
 def test_simulation_argument_validation():
     """simulations.py:1127-1153: same ValueErrors (checked before any GPU work would start)."""
     from disimpy_b200 import _lib, gradients, simulations, substrates
