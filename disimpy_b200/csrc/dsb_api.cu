@@ -941,6 +941,8 @@ struct dsb_sim {
     // mesh walk with the walkers in cell order (resort_interval, sort_walkers); allocated at the first sort
     int *d_order = nullptr, *d_key = nullptr, *d_bins = nullptr;
     dsb::CellBins bins{};
+    int64_t sorted_at = -1;   // time step at which d_order was made from the positions (-1: no order since the last rewind)
+    bool sort_off = false;    // no room for the sort's buffers: index order from now on
     bool signal_from_phases = false;   // the launch that reached the last step left the signal partials to phases_signal_kernel
     int rank = 0;            // > 0: low-rank protocol, the walk carries `rank` virtual measurements
     double *d_u = nullptr;   // (n_meas, rank) coefficients of the real measurements
@@ -1326,6 +1328,7 @@ static int rewind_sim(dsb_sim *s)
     s->pending.clear();
     DSB_CUDA(cudaEventRecord(s->ev_rewind, s->stream));
     s->t_cur = 0;
+    s->sorted_at = -1;
     s->parts_done = 0;
     s->part_parity = 0;
     s->kernel_ms = 0.0;
@@ -1375,7 +1378,7 @@ int dsb_set_positions_dev(dsb_sim *s, const double *positions_dev)
 static int64_t resort_interval(const dsb_sim *s)
 {
     const dsb_params &P = s->prm;
-    if (P.substrate != DSB_MESH) return 0;
+    if (P.substrate != DSB_MESH || s->sort_off) return 0;
     const int meas = s->rank > 0 ? s->rank : (int)P.n_meas;
     if (meas > dsb::kMaxRegMeas || P.n_walkers >= (int64_t(1) << 31)) return 0;
     if (const char *env = getenv("DISIMPY_B200_RESORT")) return std::max<int64_t>(0, atoll(env));
@@ -1393,7 +1396,7 @@ static int sort_walkers(dsb_sim *s, cudaStream_t st)
 {
     const int64_t N = s->prm.n_walkers;
     const dsb::MeshDev &m = s->mesh->dev;
-    if (!s->d_order) {
+    if (!s->d_order || !s->d_key || !s->d_bins) {
         const int len[3] = {m.len_xs - 1, m.len_ys - 1, m.len_zs - 1};
         for (int a = 0; a < 3; ++a) {
             s->bins.n[a] = std::max(1, std::min(len[a], 128));
@@ -1402,26 +1405,36 @@ static int sort_walkers(dsb_sim *s, cudaStream_t st)
         }
         // consecutive blocks share a slab across the longest edge of the voxel
         std::stable_sort(s->bins.axis, s->bins.axis + 3, [&](int a, int b) { return m.vox[a] > m.vox[b]; });
-        DSB_CUDA(cache_malloc(&s->d_order, sizeof(int) * N));
-        DSB_CUDA(cache_malloc(&s->d_key, sizeof(int) * N));
-        DSB_CUDA(cache_malloc(&s->d_bins, sizeof(int) * s->bins.n[0] * s->bins.n[1] * s->bins.n[2]));
+        if (!s->d_order) DSB_CUDA(cache_malloc(&s->d_order, sizeof(int) * N));
+        if (!s->d_key) DSB_CUDA(cache_malloc(&s->d_key, sizeof(int) * N));
+        if (!s->d_bins) DSB_CUDA(cache_malloc(&s->d_bins, sizeof(int) * s->bins.n[0] * s->bins.n[1] * s->bins.n[2]));
     }
     const int n_bins = s->bins.n[0] * s->bins.n[1] * s->bins.n[2];
     const unsigned blocks = (unsigned)((N + 255) / 256);
+    cudaEvent_t e0, e1;   // (counted into the run's device time like the walk launches)
+    DSB_CUDA(cudaEventCreate(&e0));
+    DSB_CUDA(cudaEventCreate(&e1));
+    DSB_CUDA(cudaEventRecord(e0, st));
     DSB_CUDA(cudaMemsetAsync(s->d_bins, 0, sizeof(int) * n_bins, st));
     dsb::cell_order_count<<<blocks, 256, 0, st>>>(s->d_pos, N, s->bins, s->d_key, s->d_bins);
     dsb::cell_order_scan<<<1, 1024, 0, st>>>(s->d_bins, n_bins);
     dsb::cell_order_scatter<<<blocks, 256, 0, st>>>(s->d_key, N, s->d_bins, s->d_order);
     DSB_CUDA(cudaGetLastError());
+    DSB_CUDA(cudaEventRecord(e1, st));
+    s->pending.emplace_back(e0, e1);
     s->n_launches += 3;
     return DSB_OK;
 }
 
 // one launch of the walk kernel: walkers [w0, w1) over time steps [t0, t1); `sorted`: all walkers
-// of the handle, assigned to threads in cell order (the sort is part of the timed launch)
+// of the handle, assigned to threads in the order of d_order
 static int launch_walk_range(dsb_sim *s, cudaStream_t st, int64_t w0, int64_t w1, int64_t t0, int64_t t1, bool sorted = false)
 {
     const dsb_params &P = s->prm;
+    cudaEvent_t e0, e1;
+    DSB_CUDA(cudaEventCreate(&e0));
+    DSB_CUDA(cudaEventCreate(&e1));
+    DSB_CUDA(cudaEventRecord(e0, st));
     dsb::KParams kp{};
     kp.n_walkers = P.n_walkers;
     kp.w_begin = w0;
@@ -1451,19 +1464,7 @@ static int launch_walk_range(dsb_sim *s, cudaStream_t st, int64_t w0, int64_t w1
     kp.mesh = s->mesh->dev;
     kp.mesh.perm_prob = s->perm_prob;   // (the upload may be shared with handles of another permeability)
     const int grid = (int)((w1 - w0 + dsb::kBlock - 1) / dsb::kBlock);
-    cudaEvent_t e0, e1;
-    DSB_CUDA(cudaEventCreate(&e0));
-    DSB_CUDA(cudaEventCreate(&e1));
-    DSB_CUDA(cudaEventRecord(e0, st));
-    if (sorted) {
-        int rc = sort_walkers(s, st);
-        if (rc) {
-            cudaEventDestroy(e0);
-            cudaEventDestroy(e1);
-            return rc;
-        }
-        kp.order = s->d_order;
-    }
+    if (sorted) kp.order = s->d_order;
     switch (P.substrate) {
     case DSB_FREE: launch_walk<0>(kp, grid, st); break;
     case DSB_SPHERE: launch_walk<1>(kp, grid, st); break;
@@ -1529,13 +1530,31 @@ int dsb_run(dsb_sim *s, int64_t t0, int64_t t1)
     Range nvtx("dsb_run: walk (+ signal reduction)");
     DSB_CUDA(cudaSetDevice(s->prm.device));
     int rc = DSB_OK;
+    int64_t a = t0;
     const int64_t resort = resort_interval(s);
-    if (resort > 0 && t1 - t0 >= std::min<int64_t>(resort, 64)) {   // (short calls -- trajectories, a few steps -- are not worth a sort)
-        for (int64_t a = t0; a < t1 && !rc; a += resort)
-            rc = launch_walk_range(s, s->stream, 0, s->prm.n_walkers, a, std::min<int64_t>(a + resort, t1), true);
-    } else {
-        rc = launch_walk_range(s, s->stream, 0, s->prm.n_walkers, t0, t1);
+    // The order made at one call serves the following ones (it is a permutation of the walkers whatever
+    // happened to them since); calls of a few steps that find none -- a trajectory written step by
+    // step -- walk in index order.
+    if (resort > 0 && (s->sorted_at >= 0 || t1 - t0 >= std::min<int64_t>(resort, 8))) {
+        while (a < t1 && !rc) {
+            if (s->sorted_at < 0 || a - s->sorted_at >= resort) {
+                rc = sort_walkers(s, s->stream);
+                if (rc == DSB_ENOMEM) {   // the cell order is an optimisation: without room for it, index order
+                    cudaGetLastError();
+                    s->sort_off = true;
+                    s->sorted_at = -1;
+                    rc = DSB_OK;
+                    break;
+                }
+                if (rc) break;
+                s->sorted_at = a;
+            }
+            const int64_t b = std::min<int64_t>(t1, s->sorted_at + resort);
+            rc = launch_walk_range(s, s->stream, 0, s->prm.n_walkers, a, b, true);
+            a = b;
+        }
     }
+    if (!rc && a < t1) rc = launch_walk_range(s, s->stream, 0, s->prm.n_walkers, a, t1);
     if (rc) return rc;
     if (t1 == s->prm.n_t) {
         rc = launch_signal_reduction(s);
