@@ -1404,15 +1404,15 @@ __global__ void ellipsoid_consts_kernel(double a0, double a1, double a2, Ellipso
 // The walk's device functions on rows of arguments, the way the reference's unit tests call its
 // `_cuda_*` functions through small test kernels (disimpy/tests/test_simulations.py:23-360);
 // layouts in include/disimpy_b200.h (dsb_selftest_device_function).
-constexpr int kUnitOps = 11;
+constexpr int kUnitOps = 15;
 __host__ __device__ constexpr int unit_n_in(int op)
 {
-    constexpr int n[kUnitOps] = {6, 6, 3, 9, 12, 5, 7, 9, 15, 11, 11};
+    constexpr int n[kUnitOps] = {6, 6, 3, 9, 12, 5, 7, 9, 15, 11, 11, 19, 19, 19, 19};
     return n[op];
 }
 __host__ __device__ constexpr int unit_n_out(int op)
 {
-    constexpr int n[kUnitOps] = {1, 3, 3, 3, 3, 1, 1, 1, 1, 6, 3};
+    constexpr int n[kUnitOps] = {1, 3, 3, 3, 3, 1, 1, 1, 1, 6, 3, 1, 1, 1, 1};
     return n[op];
 }
 
@@ -1459,10 +1459,26 @@ __global__ void __launch_bounds__(128) device_function_kernel(int op, long long 
         put(3, s);
         break;
     }
-    default: {
+    case 10: {
         Vec3 r0 = vec(0);
         cross_membrane(r0, vec(3), a[6], vec(7), a[10]);
         put(0, r0);
+        break;
+    }
+    default: {   // 11-14: the subvoxel range lookups, from the guess-and-fix-up searches the mesh walk uses
+        const double *xs = a + 3;
+        const int len = (int)a[2];
+        const double V = fabs(xs[len - 1] - xs[0]), inv_h = (double)(len - 1) / (xs[len - 1] - xs[0]);
+        const bool upper = op == 12 || op == 14;
+        const double x = upper ? fmax(a[0], a[1]) : fmin(a[0], a[1]);
+        if (op <= 12) {
+            o[0] = (double)(upper ? ul_overlap(xs, len, x, inv_h) : ll_overlap(xs, len, x, inv_h));
+        } else {
+            double nq;
+            int base;
+            axis_limit(xs, len, V, 1.0 / V, inv_h, x, upper, nq, base);
+            o[0] = (double)__double2ll_rz(fma_(nq, (double)(len - 1), (double)base));
+        }
         break;
     }
     }

@@ -77,7 +77,9 @@ def _ptr(a):
 UNIT_OPS = {"dot_product": (0, 6, 1), "cross_product": (1, 6, 3), "normalize_vector": (2, 3, 3),
             "triangle_normal": (3, 9, 3), "mat_mul": (4, 12, 3), "line_circle_intersection": (5, 5, 1),
             "line_sphere_intersection": (6, 7, 1), "line_ellipsoid_intersection": (7, 9, 1),
-            "ray_triangle_intersection_check": (8, 15, 1), "reflection": (9, 11, 6), "crossing": (10, 11, 3)}
+            "ray_triangle_intersection_check": (8, 15, 1), "reflection": (9, 11, 6), "crossing": (10, 11, 3),
+            "ll_subvoxel_overlap": (11, 19, 1), "ul_subvoxel_overlap": (12, 19, 1),
+            "ll_subvoxel_overlap_periodic": (13, 19, 1), "ul_subvoxel_overlap_periodic": (14, 19, 1)}
 
 
 def unit(name, args):

@@ -178,4 +178,58 @@ def device_function_random_rows(name, n, seed=5):
         return rows
     if name in ("reflection", "crossing"):
         return np.hstack([u(n, 3) * 1e-5, unit_vec(), rs.random_sample((n, 1)) * 1e-6, unit_vec(), np.full((n, 1), 1e-13)])
+    if name.endswith("subvoxel_overlap") or name.endswith("subvoxel_overlap_periodic"):
+        # np.linspace boundaries like substrates.mesh makes them (2 to 16 of them), a few stretched ones;
+        # coordinates up to three voxels away on either side, on boundaries and images of boundaries
+        rows = np.zeros((n, 19))
+        for i in range(n):
+            ln = rs.randint(2, 17)
+            V = 10.0 ** rs.uniform(-6, -3)
+            xs = np.linspace(0, V, ln)
+            if i % 7 == 0 and ln > 2:
+                xs[1:-1] += rs.uniform(-0.3, 0.3, size=ln - 2) * V / (ln - 1)
+            x = rs.uniform(-3, 3, size=2) * V
+            if i % 3 == 0:
+                x[0] = xs[rs.randint(ln)] + rs.randint(-3, 4) * V
+            if i % 5 == 0:
+                x[1] = rs.randint(-3, 4) * V
+            rows[i, :2], rows[i, 2], rows[i, 3:3 + ln] = x, ln, xs
+        return rows
     raise KeyError(name)
+
+
+def subvoxel_overlap_restated(name, row):
+    """disimpy/simulations.py:616-679 in plain Python (the loops as written there), for one argument row."""
+    import math
+    ln = int(row[2])
+    xs, x1, x2 = row[3:3 + ln], row[0], row[1]
+
+    def ll(xmin):
+        if xmin <= xs[0]:
+            return 0
+        if xmin >= xs[-1]:
+            return len(xs) - 1
+        for i, x in enumerate(xs):
+            if x > xmin:
+                return i - 1
+        return 0
+
+    def ul(xmax):
+        if xmax >= xs[-1]:
+            return len(xs) - 1
+        if xmax <= xs[0]:
+            return 0
+        for i, x in enumerate(xs):
+            if not x < xmax:
+                return i
+        return len(xs) - 1
+
+    if name == "ll_subvoxel_overlap":
+        return ll(min(x1, x2))
+    if name == "ul_subvoxel_overlap":
+        return ul(max(x1, x2))
+    voxel_size = abs(xs[-1] - xs[0])
+    x = min(x1, x2) if name.startswith("ll") else max(x1, x2)
+    nq = math.floor(x / voxel_size)
+    shifted = x - nq * voxel_size
+    return (ll(shifted) if name.startswith("ll") else ul(shifted)) + nq * (len(xs) - 1)

@@ -96,3 +96,22 @@ def test_device_function_known_answers():
     answers of the reference's own unit tests (disimpy/tests/test_simulations.py:23-360)."""
     from conftest import check_device_function_known_answers
     check_device_function_known_answers(O.unit)
+
+
+@pytest.mark.parametrize("name", ["ll_subvoxel_overlap", "ul_subvoxel_overlap", "ll_subvoxel_overlap_periodic",
+                                  "ul_subvoxel_overlap_periodic"])
+def test_subvoxel_overlap_functions(name):
+    """The oracle's subvoxel range lookups against the reference's loops written out in Python
+    (disimpy/simulations.py:616-679).  The periodic ones shift by fma(-voxel, n, x) in the compiled
+    kernel and by x - n * voxel in plain Python: rows where those two round differently (the shifted
+    coordinate lands on the other side of a boundary; a third of the rows sit on boundaries or their
+    periodic images on purpose) must be few and off by one; the golden trajectories pin the fma form."""
+    from conftest import device_function_random_rows, subvoxel_overlap_restated
+    rows = device_function_random_rows(name, 4000)
+    got = O.unit(name, rows)[:, 0]
+    want = np.array([subvoxel_overlap_restated(name, r) for r in rows], dtype=float)
+    differ = got != want
+    if name.endswith("periodic"):
+        assert differ.mean() < 0.05 and np.all(np.abs(got - want)[differ] <= 1)
+    else:
+        assert not differ.any()
