@@ -178,10 +178,16 @@ def _traj_line(positions):
     return memoryview(buf[:n.value])
 
 
+_TRAJ_CHUNK = 1 << 22   # values formatted per call (26 bytes of buffer each)
+
+
 def _write_traj(traj, mode, positions):
     """One line per time point: x y z of walker 1, walker 2, ... (simulations.py:1043-1048)."""
+    v = _lib.f64(positions).ravel()
     with open(traj, mode + "b") as f:
-        f.write(_traj_line(positions))
+        for a in range(0, max(v.size, 1), _TRAJ_CHUNK):
+            line = _traj_line(v[a:a + _TRAJ_CHUNK])
+            f.write(line if a + _TRAJ_CHUNK >= v.size else line[:-1])   # one newline, after the last value
 
 
 def _device_count():

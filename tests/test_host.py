@@ -330,6 +330,18 @@ def test_traj_line_equals_python_str():
         assert bytes(simulations._traj_line(part)) == want
     back = np.array(bytes(simulations._traj_line(v[:200000])).split(), dtype=float)
     assert np.array_equal(back, v[:200000])       # and every value reads back to the same double
+    # the file: one line per call, whatever the chunking
+    import tempfile
+    path = os.path.join(tempfile.mkdtemp(), "traj.txt")
+    pos = v[:3000].reshape(1000, 3)
+    old_chunk, simulations._TRAJ_CHUNK = simulations._TRAJ_CHUNK, 700
+    try:
+        simulations._write_traj(path, "w", pos)
+        simulations._write_traj(path, "a", pos[:5])
+    finally:
+        simulations._TRAJ_CHUNK = old_chunk
+    want = "".join(str(x) + " " for x in pos.ravel()) + "\n" + "".join(str(x) + " " for x in pos[:5].ravel()) + "\n"
+    assert open(path).read() == want
 
 
 def test_simulation_argument_validation():
