@@ -170,7 +170,7 @@ def add_noise_to_data(data, sigma, seed=None):
 def _traj_line(positions):
     """The text of one time point as the reference writes it (simulations.py:1043-1048): str(v) + " "
     for every value of positions.ravel(), then a newline -- formatted natively (dsb_format_traj_line:
-    the same characters, ~100 times faster than a str() per value)."""
+    the same characters, ~40 times faster than a str() per value)."""
     v = _lib.f64(positions).ravel()
     buf = np.empty(26 * v.size + 1, dtype=np.uint8)
     n = ctypes.c_int64(0)
